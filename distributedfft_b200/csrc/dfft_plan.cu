@@ -1,0 +1,1217 @@
+// dfft_plan.cu — plan construction, step schedule and execution behind include/dfft.h.
+//
+// A plan is a short list of steps — FFT passes (fft_kernels.cuh), device rendezvous kernels and NCCL
+// all-to-all-v exchanges — built once from the partition geometry, replayed by every exec:
+//
+//   reference call                                              here
+//   ------------------------------------------------------------------------------------------------
+//   cufftExecR2C/D2Z 2D (y,z)   mpicufft_slab.cpp:788           R2C z pass + C2C y pass (scattering)
+//   pack memcpy2D + Alltoallv   mpicufft_slab.cpp:646-661       fused into the y pass' stores (Peer2Peer)
+//                                                               or send slots + ncclSend/Recv (All2All)
+//   cufftExecZ2Z 1D x           mpicufft_slab.cpp:806           C2C x pass (gathering)
+//   pencil transposes 1 and 2   mpicufft_pencil.cpp:858-930,    same mechanism, row / column groups
+//                               1490-1576
+//
+// Peer2Peer: every rank maps the other ranks' work slots with CUDA IPC; an FFT pass writes its output
+// rows straight into the layout the receiver's next pass reads (NVLink stores), and ranks meet at tiny
+// flag kernels (st.release.sys / ld.acquire.sys on peer-mapped flags) instead of MPI_Waitall.
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dfft.h"
+#include "fft_kernels.cuh"
+#include "geometry.hpp"
+
+namespace dfft {
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CK_CUDA(x)                                                                                     \
+    do {                                                                                               \
+        cudaError_t e_ = (x);                                                                          \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(DFFT_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                                           std::to_string(__LINE__) + ")");                            \
+    } while (0)
+#define CK_NCCL(x)                                                                                     \
+    do {                                                                                               \
+        ncclResult_t r_ = (x);                                                                         \
+        if (r_ != ncclSuccess)                                                                         \
+            return fail(DFFT_ERR_NCCL, std::string(#x) + ": " + ncclGetErrorString(r_) + " (" + __FILE__ + ":" + \
+                                           std::to_string(__LINE__) + ")");                            \
+    } while (0)
+
+static int ilog2_exact(size_t n) {
+    if (n == 0 || (n & (n - 1))) return -1;
+    int l = 0;
+    while ((size_t(1) << l) < n) ++l;
+    return l;
+}
+
+// ---- twiddle tables ---------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t make_table(size_t count, size_t denom, void** dev) {
+    std::vector<cx<T>> h(count);
+    for (size_t m = 0; m < count; ++m) {
+        // exact symmetric evaluation in long double
+        long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)denom;
+        h[m] = cx<T>{T(cosl(a)), T(sinl(a))};
+    }
+    cudaError_t e = cudaMalloc(dev, count * sizeof(cx<T>));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dev, h.data(), count * sizeof(cx<T>), cudaMemcpyHostToDevice);
+}
+
+struct Tables {
+    int prec = DFFT_F64;
+    std::map<int, void*> tw;   // log2n -> exp(-2 pi i m / n), m < n
+    std::map<int, void*> tw2;  // log2m -> exp(-2 pi i k / 2m), k <= m/2
+    std::vector<void*> bytes;  // seg_of_n tables
+    cudaError_t get_tw(int log2n, void** out) {
+        auto it = tw.find(log2n);
+        if (it == tw.end()) {
+            void* d = nullptr;
+            size_t n = size_t(1) << log2n;
+            cudaError_t e = prec == DFFT_F64 ? make_table<double>(n, n, &d) : make_table<float>(n, n, &d);
+            if (e != cudaSuccess) return e;
+            it = tw.emplace(log2n, d).first;
+        }
+        *out = it->second;
+        return cudaSuccess;
+    }
+    cudaError_t get_tw2(int log2m, void** out) {
+        auto it = tw2.find(log2m);
+        if (it == tw2.end()) {
+            void* d = nullptr;
+            size_t m = size_t(1) << log2m;
+            cudaError_t e = prec == DFFT_F64 ? make_table<double>(m / 2 + 1, 2 * m, &d) : make_table<float>(m / 2 + 1, 2 * m, &d);
+            if (e != cudaSuccess) return e;
+            it = tw2.emplace(log2m, d).first;
+        }
+        *out = it->second;
+        return cudaSuccess;
+    }
+    cudaError_t seg_table(const Split& s, const unsigned char** out) {
+        size_t n = s.start.back() + s.size.back();
+        std::vector<unsigned char> h(n);
+        for (size_t p = 0; p < s.size.size(); ++p)
+            for (size_t k = 0; k < s.size[p]; ++k) h[s.start[p] + k] = (unsigned char)p;
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, n ? n : 1);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpy(d, h.data(), n, cudaMemcpyHostToDevice);
+        bytes.push_back(d);
+        *out = (const unsigned char*)d;
+        return e;
+    }
+    void release() {
+        for (auto& kv : tw) cudaFree(kv.second);
+        for (auto& kv : tw2) cudaFree(kv.second);
+        for (void* p : bytes) cudaFree(p);
+        tw.clear(); tw2.clear(); bytes.clear();
+    }
+};
+
+// ---- device rendezvous ---------------------------------------------------------------------------------
+// flags layout (uint64): [phase][rank], NPHASE phases.  Thread i handles group member i: publishes my
+// epoch in the peer's flag row, then waits for the peer's epoch in mine.
+constexpr int NPHASE = 4;
+__global__ void rendezvous_kernel(unsigned long long* const* peer_flags, unsigned long long* my_flags, const int* group,
+                                  int gsize, int me, int nranks, int phase, unsigned long long epoch, int* err,
+                                  long long timeout_cycles) {
+    const int i = threadIdx.x;
+    if (i >= gsize) return;
+    const int q = group[i];
+    if (q == me) return;
+    __threadfence_system();
+    unsigned long long* dst = peer_flags[q] + size_t(phase) * nranks + me;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(epoch) : "memory");
+    const unsigned long long* src = my_flags + size_t(phase) * nranks + q;
+    const long long t0 = clock64();
+    unsigned long long v;
+    while (true) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+        if (v >= epoch) break;
+        if (clock64() - t0 > timeout_cycles) {
+            atomicExch(err, 1 + phase);
+            break;
+        }
+        __nanosleep(64);
+    }
+}
+
+}  // namespace dfft
+
+using namespace dfft;
+
+struct dfft_comm_s {
+    int rank = 0, nranks = 1, device = 0;
+    ncclComm_t nccl = nullptr;
+};
+
+namespace dfft {
+
+enum StepType { STEP_PASS = 0, STEP_RENDEZVOUS = 1, STEP_A2A = 2 };
+
+struct Step {
+    StepType type = STEP_PASS;
+    const char* phase = nullptr;  // timer section recorded after this step
+    // PASS
+    PassKind kind = PASS_C2C_CONTIG;
+    int log2n = 0;
+    FftParams prm{};
+    int in_user = 0, out_user = 0;  // 1: patch seg[0].base with the caller's in, 2: with the caller's out
+    // RENDEZVOUS
+    int group = 0, phase_id = 0;  // group: 0 all, 1 first transposition group, 2 second
+    // A2A
+    std::vector<size_t> scount, soff, rcount, roff;  // elements, indexed by group member
+    int send_slot = 0, recv_slot = 0;
+};
+
+struct Schedule {
+    std::vector<Step> steps;
+    bool built = false;
+};
+
+}  // namespace dfft
+
+struct dfft_plan_s {
+    dfft_comm_t comm = nullptr;
+    dfft_config cfg{};
+    std::string bench_dir;
+    Geometry g;
+    int prec = DFFT_F64;
+    size_t esize = 16;  // bytes per complex element
+    int rank = 0, P = 1;
+    size_t domain_bytes = 0;  // this rank (getDomainSize)
+    size_t slot_bytes = 0;    // uniform over ranks
+    int nslots = 2;
+    size_t work_bytes = 0;
+    void* work = nullptr;
+    bool work_owned = false;
+    bool any_direct = false;  // some transposition uses peer stores across >1 ranks
+    bool direct1 = true, direct2 = true;
+    // peer mapping
+    std::vector<std::vector<void*>> slot_ptr;  // [slot][rank]
+    std::vector<void*> opened;                 // IPC mappings to close
+    unsigned long long* flags = nullptr;       // my flags (NPHASE * P)
+    unsigned long long** peer_flags_d = nullptr;
+    std::vector<void*> opened_flags;
+    int* groups_d = nullptr;  // [3][P] group member lists on device
+    std::vector<int> grp[3];
+    int* err_d = nullptr;
+    unsigned long long epoch = 0;
+    cudaStream_t own_stream = nullptr, last_stream = nullptr;
+    Tables tabs;
+    // schedules: [fwd/inv][d-1]
+    Schedule sched[2][3];
+    // timing
+    bool timing = false;
+    std::vector<cudaEvent_t> events;
+    std::vector<const char*> ev_names;
+    std::vector<int> ev_is_fft;  // 1 fft pass, 0 exchange
+    int n_events_used = 0;
+    int last_launches = 0;
+    int execs = 0;
+};
+
+namespace dfft {
+
+// element offset helper
+static inline void* eptr(void* base, size_t elems, size_t esize) { return (char*)base + elems * esize; }
+
+static View single_view(void* base, long long sA0, long long sA1, long long sN) {
+    View v{};
+    v.seg_of_n = nullptr;
+    v.nseg = 1;
+    v.seg[0].base = base;
+    v.seg[0].sA0 = sA0;
+    v.seg[0].sA1 = sA1;
+    v.seg[0].sN = sN;
+    v.seg[0].n0 = 0;
+    return v;
+}
+
+struct Builder {
+    dfft_plan_s* p;
+    const Geometry& g;
+    int me, i, j;
+    size_t es;
+    Builder(dfft_plan_s* p_) : p(p_), g(p_->g), me(p_->rank), i(p_->g.pi(p_->rank)), j(p_->g.pj(p_->rank)), es(p_->esize) {}
+
+    void* slot(int s, int r) const { return p->slot_ptr[s][r]; }
+
+    // slot assignment: D0, D1 direct targets of transposition 1 / 2; S, R NCCL staging
+    int slotD(int t) const { return t == 1 ? d0 : d1; }
+    int d0 = 0, d1 = 1, sS = 0, sR = 1;
+
+    Step pass(PassKind kind, size_t n, const char* phase) {
+        Step s;
+        s.type = STEP_PASS;
+        s.kind = kind;
+        s.log2n = ilog2_exact(n);
+        s.phase = phase;
+        s.prm.A0 = 1; s.prm.A1 = 1; s.prm.B = 1; s.prm.inverse = 0;
+        return s;
+    }
+};
+
+}  // namespace dfft
+
+// =====================================================================================================
+// Schedule construction
+// =====================================================================================================
+namespace dfft {
+
+// Describes one transposition for view construction.
+//   axis split on the producer side ("scatter", along the producer pass' transformed axis n) and on the
+//   consumer side ("gather", along the consumer pass' transformed axis).
+struct Trans {
+    int id;                  // 1 or 2 (which rendezvous group / config method)
+    bool direct;             // peer stores vs NCCL
+    std::vector<int> ranks;  // group members, index = position along the split
+    int mypos;
+};
+
+static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc);
+
+}  // namespace dfft
+
+static int plan_setup_memory(dfft_plan_s* p, void* user_device);
+static void plan_release_memory(dfft_plan_s* p);
+
+// -----------------------------------------------------------------------------------------------------
+namespace dfft {
+
+// Fill a segmented view over group members. f(q_pos, rank) returns {base, sA0, sA1, sN, n0}.
+template <typename F>
+static void seg_view(View& v, const unsigned char* table, const std::vector<int>& ranks, F f) {
+    v.seg_of_n = table;
+    v.nseg = int(ranks.size());
+    for (size_t q = 0; q < ranks.size(); ++q) v.seg[q] = f(int(q), ranks[q]);
+    if (v.nseg == 1) v.seg_of_n = nullptr;
+}
+
+static Seg mkseg(void* base, long long sA0, long long sA1, long long sN, size_t n0) {
+    Seg s{};
+    s.base = base; s.sA0 = sA0; s.sA1 = sA1; s.sN = sN; s.n0 = int(n0);
+    return s;
+}
+
+static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
+    const Geometry& g = p->g;
+    const int me = p->rank, P = p->P;
+    const int pi = g.pi(me), pj = g.pj(me);
+    const size_t es = p->esize;
+    const bool c2c = g.transform == DFFT_C2C;
+    Tables& T = p->tabs;
+    sc.steps.clear();
+
+    auto new_pass = [&](PassKind kind, size_t n, const char* phase, Step& s) -> int {
+        s = Step();
+        s.type = STEP_PASS;
+        s.kind = kind;
+        s.phase = phase;
+        s.log2n = ilog2_exact(n);
+        if (s.log2n < 1 || s.log2n > MAX_LOG2N)
+            return fail(DFFT_ERR_UNSUPPORTED, "axis length " + std::to_string(n) + " is not a supported power of two (2..8192)");
+        s.prm.A0 = 1; s.prm.A1 = 1; s.prm.B = 1;
+        s.prm.inverse = inverse;
+        void* tw = nullptr;
+        if (T.get_tw(s.log2n, &tw) != cudaSuccess) return fail(DFFT_ERR_CUDA, "twiddle table allocation failed");
+        s.prm.tw = tw;
+        s.prm.tw2 = nullptr;
+        if (kind == PASS_R2C || kind == PASS_C2R) {
+            void* tw2 = nullptr;
+            if (T.get_tw2(s.log2n, &tw2) != cudaSuccess) return fail(DFFT_ERR_CUDA, "twiddle table allocation failed");
+            s.prm.tw2 = tw2;
+        }
+        return DFFT_SUCCESS;
+    };
+    auto rendezvous = [&](int group, int phase_id, const char* phase) {
+        Step s;
+        s.type = STEP_RENDEZVOUS;
+        s.group = group;
+        s.phase_id = phase_id;
+        s.phase = phase;
+        sc.steps.push_back(s);
+    };
+
+    // groups: transposition 1 / 2 member lists (positions along the split axis)
+    const std::vector<int>& G1 = p->grp[1];
+    const std::vector<int>& G2 = p->grp[2];
+    const bool dir1 = p->direct1 || G1.size() == 1;
+    const bool dir2 = p->direct2 || G2.size() == 1;
+    // slot ids
+    int nxt = 0;
+    int D1 = -1, D2 = -1, SS = -1, SR = -1;
+    if (dir1) D1 = nxt++;
+    if (dir2) D2 = nxt++;
+    if (!dir1 || !dir2) { SS = nxt++; SR = nxt++; }
+    auto slotp = [&](int s, int r) -> void* { return p->slot_ptr[s][r]; };
+
+    if (p->any_direct) rendezvous(0, 0, nullptr);  // everyone has left the previous exec: slots are free
+
+    const size_t nzc = g.nzc;
+    const bool zyx = g.decomp == DFFT_SLAB_Z_THEN_YX;
+    int rc;
+
+    // sizes of this rank
+    const size_t nx_i = g.sx.size[pi], x0_i = g.sx.start[pi];
+    const size_t ny_j = zyx ? g.ny : g.sy.size[pj], y0_j = zyx ? 0 : g.sy.start[pj];
+    const size_t nz_j = zyx ? g.sz.size[me] : g.sz.size[pj], z0_j = zyx ? g.sz.start[me] : g.sz.start[pj];
+    const size_t oy_i = zyx ? g.ny : g.oy.size[pi], oy0_i = zyx ? 0 : g.oy.start[pi];
+    (void)x0_i; (void)y0_j; (void)z0_j; (void)oy0_i;
+
+    const unsigned char *tab_z = nullptr, *tab_y_in = nullptr, *tab_y_out = nullptr, *tab_x = nullptr;
+    if (G1.size() > 1) {
+        if (T.seg_table(g.sz, &tab_z) != cudaSuccess) return fail(DFFT_ERR_CUDA, "segment table");
+        if (!zyx && T.seg_table(g.sy, &tab_y_in) != cudaSuccess) return fail(DFFT_ERR_CUDA, "segment table");
+    }
+    if (G2.size() > 1 || (zyx && G1.size() > 1)) {
+        if (!zyx && T.seg_table(g.oy, &tab_y_out) != cudaSuccess) return fail(DFFT_ERR_CUDA, "segment table");
+        if (T.seg_table(g.sx, &tab_x) != cudaSuccess) return fail(DFFT_ERR_CUDA, "segment table");
+    }
+
+    auto a2a_counts = [&](Step& s, const std::vector<int>& G, auto send_elems, auto recv_elems) {
+        s.type = STEP_A2A;
+        size_t so = 0, ro = 0;
+        s.scount.resize(G.size()); s.soff.resize(G.size()); s.rcount.resize(G.size()); s.roff.resize(G.size());
+        for (size_t q = 0; q < G.size(); ++q) {
+            s.scount[q] = send_elems(int(q));
+            s.rcount[q] = recv_elems(int(q));
+            s.soff[q] = so; s.roff[q] = ro;
+            so += s.scount[q]; ro += s.rcount[q];
+        }
+        s.send_slot = SS; s.recv_slot = SR;
+    };
+
+    if (!inverse) {
+        // ------------------------------------------------------------------ forward
+        // pass 1: z (contiguous), lines (x in nx_i, y in ny_j)
+        Step s1;
+        rc = new_pass(c2c ? PASS_C2C_CONTIG : PASS_R2C, c2c ? g.nz : g.nz / 2, zyx || g.decomp == DFFT_PENCIL ? "1D FFT Z-Direction" : nullptr, s1);
+        if (rc) return rc;
+        s1.prm.A0 = int(nx_i); s1.prm.A1 = int(ny_j);
+        {   // input: caller's buffer; real lines of nz reals = nz/2 complex
+            const long long pitch = c2c ? (long long)g.nz : (long long)(g.nz / 2);
+            s1.prm.in = single_view(nullptr, pitch * (long long)ny_j, pitch, 1);
+            s1.in_user = 1;
+        }
+        if (d == 1) {
+            s1.prm.out = single_view(nullptr, (long long)(ny_j * nzc), (long long)nzc, 1);
+            s1.out_user = 2;
+            sc.steps.push_back(s1);
+            sc.built = true;
+            return DFFT_SUCCESS;
+        }
+        // transposition 1: scatter along z over G1
+        Step x1;  // optional a2a
+        const bool t1_a2a = !dir1;
+        if (zyx) {
+            // x split -> z split: dest q holds [nx][ny][nz_q]
+            if (dir1) {
+                seg_view(s1.prm.out, tab_z, G1, [&](int q, int r) {
+                    const size_t nzq = g.sz.size[q];
+                    return mkseg(eptr(slotp(D1, r), g.sx.start[me] * g.ny * nzq, es), (long long)(g.ny * nzq), (long long)nzq, 1, g.sz.start[q]);
+                });
+            } else {
+                a2a_counts(x1, G1, [&](int q) { return nx_i * g.ny * g.sz.size[q]; }, [&](int q) { return g.sx.size[q] * g.ny * nz_j; });
+                seg_view(s1.prm.out, tab_z, G1, [&](int q, int) {
+                    const size_t nzq = g.sz.size[q];
+                    return mkseg(eptr(slotp(SS, me), x1.soff[q], es), (long long)(g.ny * nzq), (long long)nzq, 1, g.sz.start[q]);
+                });
+            }
+        } else {
+            // pencil row: dest (i,q) holds [nx_i][ny][nz_q]
+            if (dir1) {
+                seg_view(s1.prm.out, tab_z, G1, [&](int q, int r) {
+                    const size_t nzq = g.sz.size[q];
+                    return mkseg(eptr(slotp(D1, r), y0_j * nzq, es), (long long)(g.ny * nzq), (long long)nzq, 1, g.sz.start[q]);
+                });
+            } else {
+                a2a_counts(x1, G1, [&](int q) { return nx_i * ny_j * g.sz.size[q]; }, [&](int q) { return nx_i * g.sy.size[q] * nz_j; });
+                seg_view(s1.prm.out, tab_z, G1, [&](int q, int) {
+                    const size_t nzq = g.sz.size[q];
+                    return mkseg(eptr(slotp(SS, me), x1.soff[q], es), (long long)(ny_j * nzq), (long long)nzq, 1, g.sz.start[q]);
+                });
+            }
+        }
+        if (g.decomp == DFFT_SLAB_ZY_THEN_X) s1.phase = nullptr;
+        sc.steps.push_back(s1);
+        if (t1_a2a) { x1.phase = zyx ? "Transpose (Finished All2All)" : "First Transpose (Finished All2All)"; x1.group = 1; sc.steps.push_back(x1); }
+        else if (G1.size() > 1) rendezvous(1, 1, zyx ? "Transpose (Finished Receive)" : "First Transpose (Finished Receive)");
+
+        // pass 2: y (tiled): a0 = x, n = y, b = z in nz_j
+        Step s2;
+        const size_t nx2 = zyx ? g.nx : nx_i;  // x extent held after transposition 1
+        rc = new_pass(PASS_C2C_TILED, g.ny, g.decomp == DFFT_SLAB_ZY_THEN_X ? "2D FFT Y-Z-Direction" : (zyx ? nullptr : "1D FFT Y-Direction"), s2);
+        if (rc) return rc;
+        s2.prm.A0 = int(nx2); s2.prm.A1 = 1; s2.prm.B = int(nz_j);
+        if (t1_a2a && !zyx) {
+            seg_view(s2.prm.in, tab_y_in, G1, [&](int q, int) {
+                const size_t nyq = g.sy.size[q];
+                return mkseg(eptr(slotp(SR, me), x1.roff[q], es), (long long)(nyq * nz_j), 0, (long long)nz_j, g.sy.start[q]);
+            });
+        } else {
+            void* base = t1_a2a ? slotp(SR, me) : slotp(D1, me);
+            s2.prm.in = single_view(base, (long long)(g.ny * nz_j), 0, (long long)nz_j);
+        }
+        if (d == 2 || zyx) {
+            if (d == 2) {
+                s2.prm.out = single_view(nullptr, (long long)(g.ny * nz_j), 0, (long long)nz_j);
+                s2.out_user = 2;
+                sc.steps.push_back(s2);
+                sc.built = true;
+                return DFFT_SUCCESS;
+            }
+            // z_then_yx: y pass in place, then x pass into the caller's out
+            s2.prm.out = s2.prm.in;
+            if (s2.prm.in.nseg != 1) return fail(DFFT_ERR_STATE, "internal: z_then_yx gather view");
+            sc.steps.push_back(s2);
+            Step s3;
+            rc = new_pass(PASS_C2C_TILED, g.nx, "2D FFT Y-X-Direction", s3);
+            if (rc) return rc;
+            s3.prm.A0 = 1; s3.prm.A1 = 1; s3.prm.B = int(g.ny * nz_j);
+            s3.prm.in = single_view(s2.prm.in.seg[0].base, 0, 0, (long long)(g.ny * nz_j));
+            s3.prm.out = single_view(nullptr, 0, 0, (long long)(g.ny * nz_j));
+            s3.out_user = 2;
+            sc.steps.push_back(s3);
+            sc.built = true;
+            return DFFT_SUCCESS;
+        }
+        // transposition 2: scatter along y over G2 (column of the grid, or all ranks for the slab)
+        Step x2;
+        const bool t2_a2a = !dir2;
+        if (dir2) {
+            seg_view(s2.prm.out, tab_y_out, G2, [&](int q, int r) {
+                const size_t nyq = g.oy.size[q];
+                return mkseg(eptr(slotp(D2, r), x0_i * nyq * nz_j, es), (long long)(nyq * nz_j), 0, (long long)nz_j, g.oy.start[q]);
+            });
+        } else {
+            a2a_counts(x2, G2, [&](int q) { return nx_i * g.oy.size[q] * nz_j; }, [&](int q) { return g.sx.size[q] * oy_i * nz_j; });
+            seg_view(s2.prm.out, tab_y_out, G2, [&](int q, int) {
+                const size_t nyq = g.oy.size[q];
+                return mkseg(eptr(slotp(SS, me), x2.soff[q], es), (long long)(nyq * nz_j), 0, (long long)nz_j, g.oy.start[q]);
+            });
+        }
+        sc.steps.push_back(s2);
+        const bool slab = g.decomp == DFFT_SLAB_ZY_THEN_X;
+        if (t2_a2a) { x2.phase = slab ? "Transpose (Finished All2All)" : "Second Transpose (Finished All2All)"; x2.group = 2; sc.steps.push_back(x2); }
+        else if (G2.size() > 1) rendezvous(2, 2, slab ? "Transpose (Finished Receive)" : "Second Transpose (Finished Receive)");
+
+        // pass 3: x (tiled): n = x, b = (y in oy_i, z in nz_j); received blocks are x-major => contiguous
+        Step s3;
+        rc = new_pass(PASS_C2C_TILED, g.nx, "1D FFT X-Direction", s3);
+        if (rc) return rc;
+        s3.prm.A0 = 1; s3.prm.A1 = 1; s3.prm.B = int(oy_i * nz_j);
+        s3.prm.in = single_view(t2_a2a ? slotp(SR, me) : slotp(D2, me), 0, 0, (long long)(oy_i * nz_j));
+        s3.prm.out = single_view(nullptr, 0, 0, (long long)(oy_i * nz_j));
+        s3.out_user = 2;
+        sc.steps.push_back(s3);
+        sc.built = true;
+        return DFFT_SUCCESS;
+    }
+
+    // ---------------------------------------------------------------------- inverse
+    // Reverse order: x, transposition 2', y, transposition 1', z.  Partial d: only the last d of them.
+    const PassKind zkind = c2c ? PASS_C2C_CONTIG : PASS_C2R;
+    const size_t zlen = c2c ? g.nz : g.nz / 2;
+    const long long zpitch_out = c2c ? (long long)g.nz : (long long)(g.nz / 2);  // output line pitch in complex units
+
+    if (d == 1) {
+        Step s;
+        rc = new_pass(zkind, zlen, "1D FFT Z-Direction", s);
+        if (rc) return rc;
+        s.prm.A0 = int(nx_i); s.prm.A1 = int(ny_j);
+        s.prm.in = single_view(nullptr, (long long)(ny_j * nzc), (long long)nzc, 1);
+        s.in_user = 1;
+        s.prm.out = single_view(nullptr, zpitch_out * (long long)ny_j, zpitch_out, 1);
+        s.out_user = 2;
+        sc.steps.push_back(s);
+        sc.built = true;
+        return DFFT_SUCCESS;
+    }
+
+    if (zyx) {
+        // input [nx][ny][nz_me]: y pass (to a slot), x pass scattering along x to the owners of x,
+        // then z inverse on [nx_me][ny][nzc].
+        Step sy_;
+        rc = new_pass(PASS_C2C_TILED, g.ny, nullptr, sy_);
+        if (rc) return rc;
+        const int W = dir1 ? D2 : SR;  // a local scratch slot that is not the transposition target
+        sy_.prm.A0 = int(g.nx); sy_.prm.B = int(nz_j);
+        sy_.prm.in = single_view(nullptr, (long long)(g.ny * nz_j), 0, (long long)nz_j);
+        sy_.in_user = 1;
+        sy_.prm.out = single_view(slotp(W, me), (long long)(g.ny * nz_j), 0, (long long)nz_j);
+        sc.steps.push_back(sy_);
+        Step sx_;
+        rc = new_pass(PASS_C2C_TILED, g.nx, "2D FFT Y-X-Direction", sx_);
+        if (rc) return rc;
+        sx_.prm.A0 = 1; sx_.prm.A1 = int(g.ny); sx_.prm.B = int(nz_j);
+        sx_.prm.in = single_view(slotp(W, me), 0, (long long)nz_j, (long long)(g.ny * nz_j));
+        Step xa;
+        if (dir1) {
+            seg_view(sx_.prm.out, tab_x, G1, [&](int q, int r) {
+                return mkseg(eptr(slotp(D1, r), z0_j, es), 0, (long long)nzc, (long long)(g.ny * nzc), g.sx.start[q]);
+            });
+        } else {
+            a2a_counts(xa, G1, [&](int q) { return g.sx.size[q] * g.ny * nz_j; }, [&](int q) { return nx_i * g.ny * g.sz.size[q]; });
+            seg_view(sx_.prm.out, tab_x, G1, [&](int q, int) {
+                return mkseg(eptr(slotp(SS, me), xa.soff[q], es), 0, (long long)nz_j, (long long)(g.ny * nz_j), g.sx.start[q]);
+            });
+        }
+        sc.steps.push_back(sx_);
+        if (!dir1) { xa.phase = "Transpose (Finished All2All)"; xa.group = 1; sc.steps.push_back(xa); }
+        else if (G1.size() > 1) rendezvous(1, 1, "Transpose (Finished Receive)");
+        Step sz_;
+        rc = new_pass(zkind, zlen, "1D FFT Z-Direction", sz_);
+        if (rc) return rc;
+        sz_.prm.A0 = int(nx_i); sz_.prm.A1 = int(g.ny);
+        if (dir1) sz_.prm.in = single_view(slotp(D1, me), (long long)(g.ny * nzc), (long long)nzc, 1);
+        else
+            seg_view(sz_.prm.in, tab_z, G1, [&](int q, int) {
+                const size_t nzq = g.sz.size[q];
+                return mkseg(eptr(slotp(SR, me), xa.roff[q], es), (long long)(g.ny * nzq), (long long)nzq, 1, g.sz.start[q]);
+            });
+        sz_.prm.out = single_view(nullptr, zpitch_out * (long long)g.ny, zpitch_out, 1);
+        sz_.out_user = 2;
+        sc.steps.push_back(sz_);
+        sc.built = true;
+        return DFFT_SUCCESS;
+    }
+
+    // pencil / slab zy_x inverse
+    const bool slab = g.decomp == DFFT_SLAB_ZY_THEN_X;
+    Step x2;
+    bool have_in_slot = false;  // whether the y pass input is in a slot (d == 3) or the caller's buffer (d == 2)
+    if (d == 3) {
+        Step s3;
+        rc = new_pass(PASS_C2C_TILED, g.nx, "1D FFT X-Direction", s3);
+        if (rc) return rc;
+        s3.prm.A0 = 1; s3.prm.A1 = 1; s3.prm.B = int(oy_i * nz_j);
+        s3.prm.in = single_view(nullptr, 0, 0, (long long)(oy_i * nz_j));
+        s3.in_user = 1;
+        if (dir2) {
+            // dest (q,j) holds [nx_q][ny][nz_j]; my rows y in [oy0_i, +oy_i)
+            seg_view(s3.prm.out, tab_x, G2, [&](int q, int r) {
+                return mkseg(eptr(slotp(D2, r), oy0_i * nz_j, es), 0, 0, (long long)(g.ny * nz_j), g.sx.start[q]);
+            });
+        } else {
+            a2a_counts(x2, G2, [&](int q) { return g.sx.size[q] * oy_i * nz_j; }, [&](int q) { return nx_i * g.oy.size[q] * nz_j; });
+            seg_view(s3.prm.out, tab_x, G2, [&](int q, int) {
+                return mkseg(eptr(slotp(SS, me), x2.soff[q], es), 0, 0, (long long)(oy_i * nz_j), g.sx.start[q]);
+            });
+        }
+        sc.steps.push_back(s3);
+        if (!dir2) { x2.phase = slab ? "Transpose (Finished All2All)" : "Second Transpose (Finished All2All)"; x2.group = 2; sc.steps.push_back(x2); }
+        else if (G2.size() > 1) rendezvous(2, 2, slab ? "Transpose (Finished Receive)" : "Second Transpose (Finished Receive)");
+        have_in_slot = true;
+    }
+    // y pass on [nx_i][ny][nz_j]
+    Step s2;
+    rc = new_pass(PASS_C2C_TILED, g.ny, slab ? nullptr : "1D FFT Y-Direction", s2);
+    if (rc) return rc;
+    s2.prm.A0 = int(nx_i); s2.prm.A1 = 1; s2.prm.B = int(nz_j);
+    if (!have_in_slot) {
+        s2.prm.in = single_view(nullptr, (long long)(g.ny * nz_j), 0, (long long)nz_j);
+        s2.in_user = 1;
+    } else if (dir2) {
+        s2.prm.in = single_view(slotp(D2, me), (long long)(g.ny * nz_j), 0, (long long)nz_j);
+    } else {
+        seg_view(s2.prm.in, tab_y_out, G2, [&](int q, int) {
+            const size_t nyq = g.oy.size[q];
+            return mkseg(eptr(slotp(SR, me), x2.roff[q], es), (long long)(nyq * nz_j), 0, (long long)nz_j, g.oy.start[q]);
+        });
+    }
+    Step x1;
+    if (dir1) {
+        // dest (i,q) holds [nx_i][ny_q][nzc]; my columns z in [z0_j, +nz_j)
+        seg_view(s2.prm.out, tab_y_in, G1, [&](int q, int r) {
+            const size_t nyq = g.sy.size[q];
+            return mkseg(eptr(slotp(D1, r), z0_j, es), (long long)(nyq * nzc), 0, (long long)nzc, g.sy.start[q]);
+        });
+    } else {
+        a2a_counts(x1, G1, [&](int q) { return nx_i * g.sy.size[q] * nz_j; }, [&](int q) { return nx_i * ny_j * g.sz.size[q]; });
+        seg_view(s2.prm.out, tab_y_in, G1, [&](int q, int) {
+            const size_t nyq = g.sy.size[q];
+            return mkseg(eptr(slotp(SS, me), x1.soff[q], es), (long long)(nyq * nz_j), 0, (long long)nz_j, g.sy.start[q]);
+        });
+    }
+    sc.steps.push_back(s2);
+    if (!dir1) { x1.phase = "First Transpose (Finished All2All)"; x1.group = 1; sc.steps.push_back(x1); }
+    else if (G1.size() > 1) rendezvous(1, 1, "First Transpose (Finished Receive)");
+    // z pass on [nx_i][ny_j][nzc]
+    Step s1;
+    rc = new_pass(zkind, zlen, slab ? "2D FFT Y-Z-Direction" : "1D FFT Z-Direction", s1);
+    if (rc) return rc;
+    s1.prm.A0 = int(nx_i); s1.prm.A1 = int(ny_j);
+    if (dir1) s1.prm.in = single_view(slotp(D1, me), (long long)(ny_j * nzc), (long long)nzc, 1);
+    else
+        seg_view(s1.prm.in, tab_z, G1, [&](int q, int) {
+            const size_t nzq = g.sz.size[q];
+            return mkseg(eptr(slotp(SR, me), x1.roff[q], es), (long long)(ny_j * nzq), (long long)nzq, 1, g.sz.start[q]);
+        });
+    s1.prm.out = single_view(nullptr, zpitch_out * (long long)ny_j, zpitch_out, 1);
+    s1.out_user = 2;
+    sc.steps.push_back(s1);
+    sc.built = true;
+    (void)P;
+    return DFFT_SUCCESS;
+}
+
+}  // namespace dfft
+
+// =====================================================================================================
+// memory / peer mapping
+// =====================================================================================================
+static int nccl_allgather_bytes(dfft_plan_s* p, const void* mine, size_t bytes, std::vector<char>& all) {
+    const int P = p->P;
+    all.assign(bytes * P, 0);
+    if (P == 1) {
+        memcpy(all.data(), mine, bytes);
+        return DFFT_SUCCESS;
+    }
+    char* d = nullptr;
+    CK_CUDA(cudaMalloc(&d, bytes * (P + 1)));
+    CK_CUDA(cudaMemcpy(d + bytes * P, mine, bytes, cudaMemcpyHostToDevice));
+    CK_NCCL(ncclAllGather(d + bytes * P, d, bytes, ncclChar, p->comm->nccl, p->own_stream));
+    CK_CUDA(cudaStreamSynchronize(p->own_stream));
+    CK_CUDA(cudaMemcpy(all.data(), d, bytes * P, cudaMemcpyDeviceToHost));
+    CK_CUDA(cudaFree(d));
+    return DFFT_SUCCESS;
+}
+
+static void plan_release_memory(dfft_plan_s* p) {
+    for (void* q : p->opened) cudaIpcCloseMemHandle(q);
+    p->opened.clear();
+    if (p->work && p->work_owned) cudaFree(p->work);
+    p->work = nullptr;
+    p->work_owned = false;
+    p->slot_ptr.clear();
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 3; ++b) p->sched[a][b] = Schedule();
+}
+
+static int plan_setup_memory(dfft_plan_s* p, void* user_device) {
+    plan_release_memory(p);
+    const int P = p->P, me = p->rank;
+    if (user_device) {
+        p->work = user_device;
+        p->work_owned = false;
+    } else {
+        CK_CUDA(cudaMalloc(&p->work, p->work_bytes));
+        p->work_owned = true;
+    }
+    p->slot_ptr.assign(p->nslots, std::vector<void*>(P, nullptr));
+    for (int s = 0; s < p->nslots; ++s) p->slot_ptr[s][me] = (char*)p->work + size_t(s) * p->slot_bytes;
+    if (p->any_direct) {
+        cudaIpcMemHandle_t h;
+        cudaError_t e = cudaIpcGetMemHandle(&h, p->work);
+        int ok = (e == cudaSuccess) ? 1 : 0;
+        if (!ok) cudaGetLastError();
+        struct Rec { cudaIpcMemHandle_t h; int ok; int pad[3]; } rec{};
+        rec.h = h; rec.ok = ok;
+        std::vector<char> all;
+        int rc = nccl_allgather_bytes(p, &rec, sizeof(rec), all);
+        if (rc) return rc;
+        for (int r = 0; r < P; ++r) {
+            const Rec* rr = reinterpret_cast<const Rec*>(all.data()) + r;
+            if (!rr->ok) return fail(DFFT_ERR_PEER, "rank " + std::to_string(r) + ": work area is not exportable with cudaIpcGetMemHandle "
+                                                    "(must be the base of a cudaMalloc allocation); use comm_method All2All");
+        }
+        for (int r = 0; r < P; ++r) {
+            if (r == me) continue;
+            const Rec* rr = reinterpret_cast<const Rec*>(all.data()) + r;
+            void* mapped = nullptr;
+            e = cudaIpcOpenMemHandle(&mapped, rr->h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(DFFT_ERR_PEER, std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(e));
+            }
+            p->opened.push_back(mapped);
+            for (int s = 0; s < p->nslots; ++s) p->slot_ptr[s][r] = (char*)mapped + size_t(s) * p->slot_bytes;
+        }
+    }
+    return DFFT_SUCCESS;
+}
+
+static int plan_setup_flags(dfft_plan_s* p) {
+    const int P = p->P, me = p->rank;
+    CK_CUDA(cudaMalloc(&p->flags, sizeof(unsigned long long) * NPHASE * P));
+    CK_CUDA(cudaMemset(p->flags, 0, sizeof(unsigned long long) * NPHASE * P));
+    CK_CUDA(cudaMalloc(&p->err_d, sizeof(int)));
+    CK_CUDA(cudaMemset(p->err_d, 0, sizeof(int)));
+    std::vector<unsigned long long*> pf(P, nullptr);
+    pf[me] = p->flags;
+    if (p->any_direct) {
+        cudaIpcMemHandle_t h;
+        CK_CUDA(cudaIpcGetMemHandle(&h, p->flags));
+        std::vector<char> all;
+        int rc = nccl_allgather_bytes(p, &h, sizeof(h), all);
+        if (rc) return rc;
+        for (int r = 0; r < P; ++r) {
+            if (r == me) continue;
+            void* mapped = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&mapped, reinterpret_cast<const cudaIpcMemHandle_t*>(all.data())[r], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(DFFT_ERR_PEER, std::string("cudaIpcOpenMemHandle(flags) failed: ") + cudaGetErrorString(e));
+            }
+            p->opened_flags.push_back(mapped);
+            pf[r] = (unsigned long long*)mapped;
+        }
+    }
+    CK_CUDA(cudaMalloc(&p->peer_flags_d, sizeof(void*) * P));
+    CK_CUDA(cudaMemcpy(p->peer_flags_d, pf.data(), sizeof(void*) * P, cudaMemcpyHostToDevice));
+    std::vector<int> gl(3 * P, 0);
+    for (int k = 0; k < 3; ++k)
+        for (size_t q = 0; q < p->grp[k].size(); ++q) gl[k * P + q] = p->grp[k][q];
+    CK_CUDA(cudaMalloc(&p->groups_d, sizeof(int) * 3 * P));
+    CK_CUDA(cudaMemcpy(p->groups_d, gl.data(), sizeof(int) * 3 * P, cudaMemcpyHostToDevice));
+    return DFFT_SUCCESS;
+}
+
+// =====================================================================================================
+// execution
+// =====================================================================================================
+static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in, cudaStream_t st) {
+    const int P = p->P, me = p->rank;
+    const size_t es = p->esize;
+    p->epoch++;
+    p->last_stream = st;
+    int launches = 0;
+    int ev = 0;
+    const bool timing = p->timing;
+    auto mark = [&](const char* name, int is_fft) -> cudaError_t {
+        if (!timing) return cudaSuccess;
+        if (ev >= int(p->events.size())) {
+            cudaEvent_t e;
+            cudaError_t r = cudaEventCreate(&e);
+            if (r != cudaSuccess) return r;
+            p->events.push_back(e);
+            p->ev_names.push_back(name);
+            p->ev_is_fft.push_back(is_fft);
+        }
+        p->ev_names[ev] = name;
+        p->ev_is_fft[ev] = is_fft;
+        return cudaEventRecord(p->events[ev++], st);
+    };
+    CK_CUDA(mark("start", -1));
+    for (Step& s : sc.steps) {
+        if (s.type == STEP_PASS) {
+            FftParams prm = s.prm;
+            if (s.in_user == 1) prm.in.seg[0].base = const_cast<void*>(in);
+            if (s.out_user == 2) prm.out.seg[0].base = out;
+            cudaError_t e = p->prec == DFFT_F64 ? launch_pass_f64(s.log2n, s.kind, prm, st) : launch_pass_f32(s.log2n, s.kind, prm, st);
+            if (e != cudaSuccess) return fail(DFFT_ERR_CUDA, std::string("FFT pass launch failed: ") + cudaGetErrorString(e));
+            ++launches;
+            CK_CUDA(mark(s.phase, 1));
+        } else if (s.type == STEP_RENDEZVOUS) {
+            const std::vector<int>& G = p->grp[s.group];
+            if (G.size() > 1) {
+                rendezvous_kernel<<<1, 32 * int((G.size() + 31) / 32), 0, st>>>(p->peer_flags_d, p->flags, p->groups_d + s.group * P, int(G.size()), me, P,
+                                                                              s.phase_id, p->epoch, p->err_d, 20000000000LL);
+                CK_CUDA(cudaGetLastError());
+                ++launches;
+            }
+            CK_CUDA(mark(s.phase, 0));
+        } else {
+            const std::vector<int>& G = p->grp[s.group];
+            char* sb = (char*)p->slot_ptr[s.send_slot][me];
+            char* rb = (char*)p->slot_ptr[s.recv_slot][me];
+            CK_NCCL(ncclGroupStart());
+            for (size_t q = 0; q < G.size(); ++q) {
+                if (G[q] == me) continue;
+                if (s.scount[q]) CK_NCCL(ncclSend(sb + s.soff[q] * es, s.scount[q] * es, ncclChar, G[q], p->comm->nccl, st));
+                if (s.rcount[q]) CK_NCCL(ncclRecv(rb + s.roff[q] * es, s.rcount[q] * es, ncclChar, G[q], p->comm->nccl, st));
+            }
+            CK_NCCL(ncclGroupEnd());
+            for (size_t q = 0; q < G.size(); ++q)
+                if (G[q] == me && s.scount[q])
+                    CK_CUDA(cudaMemcpyAsync(rb + s.roff[q] * es, sb + s.soff[q] * es, s.scount[q] * es, cudaMemcpyDeviceToDevice, st));
+            CK_CUDA(mark(s.phase, 0));
+        }
+    }
+    CK_CUDA(mark("Run complete", -1));
+    p->n_events_used = ev;
+    p->last_launches = launches;
+    p->execs++;
+    return DFFT_SUCCESS;
+}
+
+static int exec_common(dfft_plan_t p, void* out, const void* in, int inverse, int d, int need_transform, void* stream, bool sync) {
+    if (!p) return fail(DFFT_ERR_INVALID, "null plan");
+    if (!p->work) return fail(DFFT_ERR_STATE, "plan has no work area (call dfft_set_work_area)");
+    if (p->g.transform != need_transform) return fail(DFFT_ERR_INVALID, need_transform == DFFT_C2C ? "plan was created for R2C/C2R" : "plan was created for C2C");
+    if (d < 1 || d > 3) return fail(DFFT_ERR_INVALID, "d must be 1, 2 or 3");
+    if (!out || !in) return fail(DFFT_ERR_INVALID, "null buffer");
+    CK_CUDA(cudaSetDevice(p->comm->device));
+    Schedule& sc = p->sched[inverse ? 1 : 0][d - 1];
+    if (!sc.built) {
+        int rc = build_schedule(p, inverse ? 1 : 0, d, sc);
+        if (rc) return rc;
+    }
+    cudaStream_t st = stream ? (cudaStream_t)stream : p->own_stream;
+    int rc = run_schedule(p, sc, out, in, st);
+    if (rc) return rc;
+    if (sync) return dfft_plan_wait(p);
+    return DFFT_SUCCESS;
+}
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* dfft_last_error_string(void) { return g_err.c_str(); }
+int dfft_version(void) { return DFFT_VERSION; }
+
+int dfft_get_unique_id(void* id) {
+    if (!id) return fail(DFFT_ERR_INVALID, "null id");
+    static_assert(sizeof(ncclUniqueId) <= DFFT_UNIQUE_ID_BYTES, "unique id size");
+    ncclUniqueId u;
+    CK_NCCL(ncclGetUniqueId(&u));
+    memset(id, 0, DFFT_UNIQUE_ID_BYTES);
+    memcpy(id, &u, sizeof(u));
+    return DFFT_SUCCESS;
+}
+
+int dfft_comm_create(int rank, int nranks, const void* id, int device, dfft_comm_t* comm) {
+    if (!comm || nranks < 1 || rank < 0 || rank >= nranks) return fail(DFFT_ERR_INVALID, "bad rank / nranks");
+    if (nranks > MAXSEG) return fail(DFFT_ERR_UNSUPPORTED, "at most " + std::to_string(MAXSEG) + " ranks");
+    CK_CUDA(cudaSetDevice(device));
+    dfft_comm_s* c = new dfft_comm_s();
+    c->rank = rank; c->nranks = nranks; c->device = device;
+    if (nranks > 1) {
+        if (!id) { delete c; return fail(DFFT_ERR_INVALID, "unique id required for nranks > 1"); }
+        ncclUniqueId u;
+        memcpy(&u, id, sizeof(u));
+        ncclResult_t r = ncclCommInitRank(&c->nccl, nranks, u, rank);
+        if (r != ncclSuccess) { delete c; return fail(DFFT_ERR_NCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(r)); }
+    }
+    *comm = c;
+    return DFFT_SUCCESS;
+}
+int dfft_comm_destroy(dfft_comm_t c) {
+    if (!c) return DFFT_SUCCESS;
+    if (c->nccl) ncclCommDestroy(c->nccl);
+    delete c;
+    return DFFT_SUCCESS;
+}
+int dfft_comm_rank(dfft_comm_t c) { return c ? c->rank : -1; }
+int dfft_comm_size(dfft_comm_t c) { return c ? c->nranks : -1; }
+
+int dfft_partition(size_t n, size_t parts, size_t* sizes, size_t* starts) {
+    if (!parts || !sizes || !starts) return fail(DFFT_ERR_INVALID, "bad partition request");
+    Split s;
+    s.make(n, parts);
+    for (size_t p = 0; p < parts; ++p) { sizes[p] = s.size[p]; starts[p] = s.start[p]; }
+    return DFFT_SUCCESS;
+}
+
+int dfft_layout(int decomp, int transform, size_t nx, size_t ny, size_t nz, size_t p1, size_t p2, int rank, int which,
+                size_t size[3], size_t start[3]) {
+    Geometry g;
+    int nranks = decomp == DFFT_PENCIL ? int(p1 * p2) : int(p1);
+    if (!g.init(decomp, transform, nx, ny, nz, p1, p2, nranks)) return fail(DFFT_ERR_INVALID, "invalid partition");
+    if (rank < 0 || rank >= nranks || which < 0 || which > 3) return fail(DFFT_ERR_INVALID, "bad rank / which");
+    g.layout(rank, which, size, start);
+    return DFFT_SUCCESS;
+}
+
+int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, int precision, int transform, size_t nx, size_t ny,
+                     size_t nz, size_t p1, size_t p2, int allocate, dfft_plan_t* plan) {
+    if (!comm || !plan) return fail(DFFT_ERR_INVALID, "null comm / plan");
+    if (precision != DFFT_F32 && precision != DFFT_F64) return fail(DFFT_ERR_INVALID, "bad precision");
+    if (transform != DFFT_R2C && transform != DFFT_C2C) return fail(DFFT_ERR_INVALID, "bad transform");
+    CK_CUDA(cudaSetDevice(comm->device));
+    dfft_plan_s* p = new dfft_plan_s();
+    p->comm = comm;
+    if (config) {
+        p->cfg = *config;
+        if (config->benchmark_dir) p->bench_dir = config->benchmark_dir;
+        p->cfg.benchmark_dir = nullptr;
+    } else {
+        p->cfg.comm_method = DFFT_PEER2PEER; p->cfg.comm_method2 = DFFT_PEER2PEER;
+    }
+    p->rank = comm->rank; p->P = comm->nranks;
+    p->prec = precision;
+    p->esize = precision == DFFT_F64 ? 16 : 8;
+    p->tabs.prec = precision;
+    if (!p->g.init(decomp, transform, nx, ny, nz, p1, p2, p->P)) {
+        delete p;
+        return fail(DFFT_ERR_INVALID, "invalid partition: P1*P2 must equal the communicator size");
+    }
+    const Geometry& g = p->g;
+    if (ilog2_exact(nx) < 1 || ilog2_exact(ny) < 1 || ilog2_exact(nz) < 1 || ilog2_exact(nx) > MAX_LOG2N || ilog2_exact(ny) > MAX_LOG2N ||
+        ilog2_exact(nz) > MAX_LOG2N + (transform == DFFT_R2C ? 1 : 0) || (transform == DFFT_R2C && nz < 4)) {
+        delete p;
+        return fail(DFFT_ERR_UNSUPPORTED, "Nx, Ny, Nz must be powers of two in [2, 8192] (Nz >= 4 for R2C)");
+    }
+    // every rank needs a non-empty share along each split axis
+    if (g.sx.size.back() == 0 || g.sy.size.back() == 0 || g.sz.size.back() == 0 || g.oy.size.back() == 0) {
+        delete p;
+        return fail(DFFT_ERR_INVALID, "partition leaves a rank without data");
+    }
+    // groups
+    const int me = p->rank, P = p->P;
+    p->grp[0].clear();
+    for (int r = 0; r < P; ++r) p->grp[0].push_back(r);
+    if (decomp == DFFT_PENCIL) {
+        const int i = g.pi(me), j = g.pj(me);
+        for (int q = 0; q < g.P2; ++q) p->grp[1].push_back(i * g.P2 + q);
+        for (int q = 0; q < g.P1; ++q) p->grp[2].push_back(q * g.P2 + j);
+    } else if (decomp == DFFT_SLAB_ZY_THEN_X) {
+        p->grp[1].push_back(me);
+        p->grp[2] = p->grp[0];
+    } else {
+        p->grp[1] = p->grp[0];
+        p->grp[2].push_back(me);
+    }
+    p->direct1 = p->cfg.comm_method != DFFT_ALL2ALL;
+    p->direct2 = (decomp == DFFT_PENCIL ? p->cfg.comm_method2 : p->cfg.comm_method) != DFFT_ALL2ALL;
+    if (decomp == DFFT_SLAB_ZY_THEN_X) p->direct1 = true;   // trivial group
+    if (decomp == DFFT_SLAB_Z_THEN_YX) p->direct2 = true;
+    const bool d1 = p->direct1 || p->grp[1].size() == 1, d2 = p->direct2 || p->grp[2].size() == 1;
+    p->any_direct = (p->direct1 && p->grp[1].size() > 1) || (p->direct2 && p->grp[2].size() > 1);
+    p->nslots = (d1 ? 1 : 0) + (d2 ? 1 : 0) + ((!d1 || !d2) ? 2 : 0);
+    if (p->nslots < 2) p->nslots = 2;
+    size_t dom = 0;
+    for (int r = 0; r < P; ++r) dom = std::max(dom, g.domain_elems(r));
+    p->domain_bytes = g.domain_elems(me) * p->esize;
+    p->slot_bytes = ((dom * p->esize + 255) / 256) * 256;
+    p->work_bytes = p->slot_bytes * p->nslots;
+    cudaError_t ce = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) { delete p; return fail(DFFT_ERR_CUDA, "cudaStreamCreate failed"); }
+    int rc = plan_setup_flags(p);
+    if (rc == DFFT_SUCCESS && allocate) rc = plan_setup_memory(p, nullptr);
+    if (rc != DFFT_SUCCESS) {
+        std::string keep = g_err;
+        dfft_plan_destroy(p);
+        g_err = keep;
+        return rc;
+    }
+    *plan = p;
+    return DFFT_SUCCESS;
+}
+
+int dfft_plan_destroy(dfft_plan_t p) {
+    if (!p) return DFFT_SUCCESS;
+    cudaSetDevice(p->comm->device);
+    cudaDeviceSynchronize();
+    plan_release_memory(p);
+    for (void* q : p->opened_flags) cudaIpcCloseMemHandle(q);
+    if (p->flags) cudaFree(p->flags);
+    if (p->peer_flags_d) cudaFree(p->peer_flags_d);
+    if (p->groups_d) cudaFree(p->groups_d);
+    if (p->err_d) cudaFree(p->err_d);
+    p->tabs.release();
+    for (cudaEvent_t e : p->events) cudaEventDestroy(e);
+    if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    delete p;
+    return DFFT_SUCCESS;
+}
+
+int dfft_set_work_area(dfft_plan_t p, void* device, void* host) {
+    (void)host;
+    if (!p) return fail(DFFT_ERR_INVALID, "null plan");
+    CK_CUDA(cudaSetDevice(p->comm->device));
+    CK_CUDA(cudaDeviceSynchronize());
+    return plan_setup_memory(p, device);
+}
+
+int dfft_exec_r2c(dfft_plan_t p, void* out, const void* in) { return exec_common(p, out, in, 0, 3, DFFT_R2C, nullptr, true); }
+int dfft_exec_c2r(dfft_plan_t p, void* out, const void* in) { return exec_common(p, out, in, 1, 3, DFFT_R2C, nullptr, true); }
+int dfft_exec_c2c(dfft_plan_t p, void* out, const void* in, int direction) {
+    return exec_common(p, out, in, direction > 0 ? 1 : 0, 3, DFFT_C2C, nullptr, true);
+}
+int dfft_exec_r2c_partial(dfft_plan_t p, void* out, const void* in, int d) { return exec_common(p, out, in, 0, d, DFFT_R2C, nullptr, true); }
+int dfft_exec_c2r_partial(dfft_plan_t p, void* out, const void* in, int d) { return exec_common(p, out, in, 1, d, DFFT_R2C, nullptr, true); }
+int dfft_exec_c2c_partial(dfft_plan_t p, void* out, const void* in, int direction, int d) {
+    return exec_common(p, out, in, direction > 0 ? 1 : 0, d, DFFT_C2C, nullptr, true);
+}
+int dfft_exec_r2c_async(dfft_plan_t p, void* out, const void* in, void* stream) { return exec_common(p, out, in, 0, 3, DFFT_R2C, stream, false); }
+int dfft_exec_c2r_async(dfft_plan_t p, void* out, const void* in, void* stream) { return exec_common(p, out, in, 1, 3, DFFT_R2C, stream, false); }
+int dfft_exec_c2c_async(dfft_plan_t p, void* out, const void* in, int direction, void* stream) {
+    return exec_common(p, out, in, direction > 0 ? 1 : 0, 3, DFFT_C2C, stream, false);
+}
+
+int dfft_plan_wait(dfft_plan_t p) {
+    if (!p) return fail(DFFT_ERR_INVALID, "null plan");
+    CK_CUDA(cudaStreamSynchronize(p->last_stream ? p->last_stream : p->own_stream));
+    int err = 0;
+    CK_CUDA(cudaMemcpy(&err, p->err_d, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) {
+        cudaMemset(p->err_d, 0, sizeof(int));
+        return fail(DFFT_ERR_TIMEOUT, "device rendezvous timed out in phase " + std::to_string(err - 1) + " (a peer rank did not arrive)");
+    }
+    return DFFT_SUCCESS;
+}
+
+static int layout_of(dfft_plan_t p, int which, size_t size[3], size_t start[3]) {
+    if (!p) return fail(DFFT_ERR_INVALID, "null plan");
+    size_t s[3], o[3];
+    p->g.layout(p->rank, which, s, o);
+    for (int k = 0; k < 3; ++k) {
+        if (size) size[k] = s[k];
+        if (start) start[k] = o[k];
+    }
+    return DFFT_SUCCESS;
+}
+int dfft_get_in_size(dfft_plan_t p, size_t size[3]) { return layout_of(p, 0, size, nullptr); }
+int dfft_get_in_start(dfft_plan_t p, size_t start[3]) { return layout_of(p, 0, nullptr, start); }
+int dfft_get_out_size(dfft_plan_t p, size_t size[3]) { return layout_of(p, 3, size, nullptr); }
+int dfft_get_out_start(dfft_plan_t p, size_t start[3]) { return layout_of(p, 3, nullptr, start); }
+int dfft_get_partial_size(dfft_plan_t p, int d, size_t size[3]) {
+    if (d < 1 || d > 3) return fail(DFFT_ERR_INVALID, "d must be 1..3");
+    return layout_of(p, d, size, nullptr);
+}
+int dfft_get_partial_start(dfft_plan_t p, int d, size_t start[3]) {
+    if (d < 1 || d > 3) return fail(DFFT_ERR_INVALID, "d must be 1..3");
+    return layout_of(p, d, nullptr, start);
+}
+size_t dfft_get_domain_size(dfft_plan_t p) { return p ? p->domain_bytes : 0; }
+size_t dfft_get_work_size_device(dfft_plan_t p) { return p ? p->work_bytes : 0; }
+size_t dfft_get_work_size_host(dfft_plan_t) { return 0; }
+void* dfft_get_work_area_device(dfft_plan_t p) { return p ? p->work : nullptr; }
+int dfft_get_rank(dfft_plan_t p) { return p ? p->rank : -1; }
+int dfft_get_world_size(dfft_plan_t p) { return p ? p->P : -1; }
+
+int dfft_timer_enable(dfft_plan_t p, int enable) {
+    if (!p) return fail(DFFT_ERR_INVALID, "null plan");
+    p->timing = enable != 0;
+    return DFFT_SUCCESS;
+}
+int dfft_get_phase_count(dfft_plan_t p) {
+    if (!p) return 0;
+    int n = 0;
+    for (int k = 1; k < p->n_events_used; ++k)
+        if (p->ev_names[k]) ++n;
+    return n;
+}
+const char* dfft_get_phase_name(dfft_plan_t p, int i) {
+    if (!p) return nullptr;
+    int n = 0;
+    for (int k = 1; k < p->n_events_used; ++k)
+        if (p->ev_names[k]) {
+            if (n == i) return p->ev_names[k];
+            ++n;
+        }
+    return nullptr;
+}
+int dfft_get_phase_times(dfft_plan_t p, double* ms, int capacity) {
+    if (!p || !ms) return fail(DFFT_ERR_INVALID, "null argument");
+    if (p->n_events_used < 2) return fail(DFFT_ERR_STATE, "no timed exec yet (dfft_timer_enable)");
+    CK_CUDA(cudaEventSynchronize(p->events[p->n_events_used - 1]));
+    int n = 0;
+    for (int k = 1; k < p->n_events_used; ++k)
+        if (p->ev_names[k]) {
+            if (n < capacity) {
+                float f = 0;
+                CK_CUDA(cudaEventElapsedTime(&f, p->events[0], p->events[k]));
+                ms[n] = f;
+            }
+            ++n;
+        }
+    return n;
+}
+int dfft_get_last_breakdown(dfft_plan_t p, double* fft_ms, double* exchange_ms, double* total_ms) {
+    if (!p) return fail(DFFT_ERR_INVALID, "null plan");
+    if (p->n_events_used < 2) return fail(DFFT_ERR_STATE, "no timed exec yet (dfft_timer_enable)");
+    CK_CUDA(cudaEventSynchronize(p->events[p->n_events_used - 1]));
+    double f = 0, x = 0;
+    for (int k = 1; k < p->n_events_used; ++k) {
+        float d = 0;
+        CK_CUDA(cudaEventElapsedTime(&d, p->events[k - 1], p->events[k]));
+        if (p->ev_is_fft[k] == 1) f += d;
+        else if (p->ev_is_fft[k] == 0) x += d;
+    }
+    float tot = 0;
+    CK_CUDA(cudaEventElapsedTime(&tot, p->events[0], p->events[p->n_events_used - 1]));
+    if (fft_ms) *fft_ms = f;
+    if (exchange_ms) *exchange_ms = x;
+    if (total_ms) *total_ms = tot;
+    return DFFT_SUCCESS;
+}
+int dfft_get_last_launch_count(dfft_plan_t p) { return p ? p->last_launches : 0; }
+
+// ---- single-axis building blocks -----------------------------------------------------------------------
+static std::map<std::pair<int, int>, void*> g_tw_cache, g_tw2_cache;  // (prec, log2n)
+
+static int cached_table(bool second, int prec, int log2n, void** out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto& cache = second ? g_tw2_cache : g_tw_cache;
+    auto key = std::make_pair(prec * 64 + dev, log2n);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        void* d = nullptr;
+        size_t n = size_t(1) << log2n;
+        cudaError_t e;
+        if (!second) e = prec == DFFT_F64 ? make_table<double>(n, n, &d) : make_table<float>(n, n, &d);
+        else e = prec == DFFT_F64 ? make_table<double>(n / 2 + 1, 2 * n, &d) : make_table<float>(n / 2 + 1, 2 * n, &d);
+        if (e != cudaSuccess) return fail(DFFT_ERR_CUDA, "twiddle table allocation failed");
+        it = cache.emplace(key, d).first;
+    }
+    *out = it->second;
+    return DFFT_SUCCESS;
+}
+
+int dfft_fft1d_contig(int precision, int kind, int direction, size_t n, size_t lines, void* out, size_t out_pitch, const void* in,
+                      size_t in_pitch, void* stream) {
+    if (precision != DFFT_F32 && precision != DFFT_F64) return fail(DFFT_ERR_INVALID, "bad precision");
+    if (kind < 0 || kind > 2) return fail(DFFT_ERR_INVALID, "bad kind");
+    const size_t len = kind == 0 ? n : n / 2;
+    const int l2 = ilog2_exact(len);
+    if (ilog2_exact(n) < 1 || l2 < 1 || l2 > MAX_LOG2N) return fail(DFFT_ERR_UNSUPPORTED, "length must be a power of two");
+    FftParams prm{};
+    prm.A0 = 1; prm.A1 = int(lines); prm.B = 1;
+    prm.inverse = (kind == 0 && direction > 0) ? 1 : 0;
+    void *tw = nullptr, *tw2 = nullptr;
+    int rc = cached_table(false, precision, l2, &tw);
+    if (rc) return rc;
+    if (kind != 0) { rc = cached_table(true, precision, l2, &tw2); if (rc) return rc; }
+    prm.tw = tw; prm.tw2 = tw2;
+    // pitches are in elements of the respective array (reals for real arrays); views are in complex units
+    long long ip = (long long)in_pitch, op = (long long)out_pitch;
+    if (kind == 1) { if (in_pitch & 1) return fail(DFFT_ERR_INVALID, "real pitch must be even"); ip /= 2; }
+    if (kind == 2) { if (out_pitch & 1) return fail(DFFT_ERR_INVALID, "real pitch must be even"); op /= 2; }
+    prm.in = single_view(const_cast<void*>(in), 0, ip, 1);
+    prm.out = single_view(out, 0, op, 1);
+    PassKind pk = kind == 0 ? PASS_C2C_CONTIG : (kind == 1 ? PASS_R2C : PASS_C2R);
+    cudaError_t e = precision == DFFT_F64 ? launch_pass_f64(l2, pk, prm, (cudaStream_t)stream) : launch_pass_f32(l2, pk, prm, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(DFFT_ERR_CUDA, std::string("launch failed: ") + cudaGetErrorString(e));
+    return DFFT_SUCCESS;
+}
+
+int dfft_fft1d_strided(int precision, int direction, size_t a, size_t n, size_t b, void* out, const void* in, void* stream) {
+    if (precision != DFFT_F32 && precision != DFFT_F64) return fail(DFFT_ERR_INVALID, "bad precision");
+    const int l2 = ilog2_exact(n);
+    if (l2 < 1 || l2 > MAX_LOG2N) return fail(DFFT_ERR_UNSUPPORTED, "length must be a power of two");
+    FftParams prm{};
+    prm.A0 = int(a); prm.A1 = 1; prm.B = int(b);
+    prm.inverse = direction > 0 ? 1 : 0;
+    void* tw = nullptr;
+    int rc = cached_table(false, precision, l2, &tw);
+    if (rc) return rc;
+    prm.tw = tw;
+    prm.in = single_view(const_cast<void*>(in), (long long)(n * b), 0, (long long)b);
+    prm.out = single_view(out, (long long)(n * b), 0, (long long)b);
+    cudaError_t e = precision == DFFT_F64 ? launch_pass_f64(l2, PASS_C2C_TILED, prm, (cudaStream_t)stream)
+                                          : launch_pass_f32(l2, PASS_C2C_TILED, prm, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(DFFT_ERR_CUDA, std::string("launch failed: ") + cudaGetErrorString(e));
+    return DFFT_SUCCESS;
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// fft_inst.cu — compiled once per (precision, log2 length): -DDFFT_T=double -DDFFT_LOG2N=10.
+// Splitting the instantiations over translation units lets build.py compile them in parallel.
+#include "fft_kernels.cuh"
+
+#ifndef DFFT_T
+#error "compile with -DDFFT_T=<float|double> -DDFFT_LOG2N=<1..13>"
+#endif
+
+namespace dfft {
+
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+}
+
+template <typename T, int LOG2N>
+cudaError_t launch_pass(PassKind kind, const FftParams& p, cudaStream_t stream) {
+    using S = Shape<T, LOG2N>;
+    constexpr int LOG2E = S::LOG2E;
+    const long long lines = (long long)p.A0 * p.A1;
+    if (lines <= 0) return cudaSuccess;
+    cudaError_t err = cudaSuccess;
+    switch (kind) {
+        case PASS_C2C_CONTIG: {
+            using C = CtaFft<T, LOG2N, LOG2E, S::TBC, false>;
+            auto k = fft_c2c_kernel<T, LOG2N, LOG2E, S::TBC, false>;
+            static cudaError_t once = set_smem(k, C::SMEM_BYTES);
+            if (once != cudaSuccess) return once;
+            const long long grid = (lines + S::TBC - 1) / S::TBC;
+            if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+            k<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
+            break;
+        }
+        case PASS_C2C_TILED: {
+            using C = CtaFft<T, LOG2N, LOG2E, S::TBT, true>;
+            auto k = fft_c2c_kernel<T, LOG2N, LOG2E, S::TBT, true>;
+            static cudaError_t once = set_smem(k, C::SMEM_BYTES);
+            if (once != cudaSuccess) return once;
+            if (p.B <= 0) return cudaSuccess;
+            const long long grid = lines * ((p.B + S::TBT - 1) / S::TBT);
+            if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+            k<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
+            break;
+        }
+        case PASS_R2C: {
+            using C = CtaFft<T, LOG2N, LOG2E, S::TBC, false>;
+            auto k = fft_r2c_kernel<T, LOG2N, LOG2E, S::TBC>;
+            static cudaError_t once = set_smem(k, C::SMEM_BYTES);
+            if (once != cudaSuccess) return once;
+            const long long grid = (lines + S::TBC - 1) / S::TBC;
+            if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+            k<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
+            break;
+        }
+        case PASS_C2R: {
+            using C = CtaFft<T, LOG2N, LOG2E, S::TBC, false>;
+            auto k = fft_c2r_kernel<T, LOG2N, LOG2E, S::TBC>;
+            static cudaError_t once = set_smem(k, C::SMEM_BYTES);
+            if (once != cudaSuccess) return once;
+            const long long grid = (lines + S::TBC - 1) / S::TBC;
+            if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+            k<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
+            break;
+        }
+        default: return cudaErrorInvalidValue;
+    }
+    err = cudaGetLastError();
+    return err;
+}
+
+template cudaError_t launch_pass<DFFT_T, DFFT_LOG2N>(PassKind, const FftParams&, cudaStream_t);
+
+}  // namespace dfft

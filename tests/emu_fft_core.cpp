@@ -1,0 +1,95 @@
+// CPU emulation of the CUDA FFT core: runs fft_core.cuh's stage arithmetic "one thread at a time" with
+// explicit exchange buffers standing in for shared memory, and checks it against a naive O(N^2) DFT.
+// Built and run by tests/test_core_emulation.py (no GPU needed). Exit code 0 = all sizes pass.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../distributedfft_b200/csrc/fft_core.cuh"
+
+using namespace dfft;
+
+template <typename T, int LOG2N, int LOG2E, int ST>
+struct RunStages {
+    using Core = FftCore<T, LOG2N, LOG2E>;
+    static void run(std::vector<cx<T>>& regs, std::vector<cx<T>>& smem, const cx<T>* tw) {
+        constexpr int E = Core::E, TPL = Core::TPL, NST = Core::NST;
+        for (int j = 0; j < TPL; ++j) {
+            cx<T>(&v)[E] = *reinterpret_cast<cx<T>(*)[E]>(&regs[size_t(j) * E]);
+            Core::template stage_compute<ST>(v, j, tw);
+        }
+        if constexpr (ST + 1 < NST) {
+            for (int j = 0; j < TPL; ++j)
+                for (int e = 0; e < E; ++e) smem[pad_idx(Core::template scatter_pos<ST>(j, e))] = regs[size_t(j) * E + e];
+            for (int j = 0; j < TPL; ++j)
+                for (int e = 0; e < E; ++e) regs[size_t(j) * E + e] = smem[pad_idx(j + e * TPL)];
+            RunStages<T, LOG2N, LOG2E, ST + 1>::run(regs, smem, tw);
+        }
+    }
+};
+
+template <typename T, int LOG2N, int LOG2E>
+double check(bool inverse) {
+    using Core = FftCore<T, LOG2N, LOG2E>;
+    constexpr int N = Core::N, E = Core::E, TPL = Core::TPL;
+    std::vector<cx<T>> x(N), out(N), regs(size_t(TPL) * E), smem(padded_len(N)), tw(N);
+    for (int m = 0; m < N; ++m) {
+        long double a = -2.0L * M_PIl * m / N;
+        tw[m] = cx<T>{T(cosl(a)), T(sinl(a))};
+    }
+    srand(1234 + LOG2N);
+    for (auto& c : x) c = cx<T>{T(rand() / double(RAND_MAX) - 0.5), T(rand() / double(RAND_MAX) - 0.5)};
+    for (int j = 0; j < TPL; ++j)
+        for (int e = 0; e < E; ++e) regs[size_t(j) * E + e] = inverse ? cswap(x[j + e * TPL]) : x[j + e * TPL];
+    RunStages<T, LOG2N, LOG2E, 0>::run(regs, smem, tw.data());
+    for (int j = 0; j < TPL; ++j)
+        for (int e = 0; e < E; ++e) {
+            cx<T> r = regs[size_t(j) * E + Core::final_slot(e)];
+            out[j + e * TPL] = inverse ? cswap(r) : r;
+        }
+    // naive DFT in long double
+    double num = 0, den = 0;
+    const double sgn = inverse ? 1.0 : -1.0;
+    for (int k = 0; k < N; ++k) {
+        long double sr = 0, si = 0;
+        for (int n = 0; n < N; ++n) {
+            long double a = sgn * 2.0L * M_PIl * ((long long)k * n % N) / N;
+            long double c = cosl(a), s = sinl(a);
+            sr += x[n].x * c - x[n].y * s;
+            si += x[n].x * s + x[n].y * c;
+        }
+        num += double((out[k].x - sr) * (out[k].x - sr) + (out[k].y - si) * (out[k].y - si));
+        den += double(sr * sr + si * si);
+    }
+    return std::sqrt(num / den);
+}
+
+static int fails = 0;
+template <typename T, int LOG2N, int LOG2E>
+void one(double tol) {
+    for (int inv = 0; inv < 2; ++inv) {
+        double e = check<T, LOG2N, LOG2E>(inv);
+        bool ok = e < tol;
+        printf("%s N=2^%d E=2^%d %s relL2=%.3e %s\n", sizeof(T) == 8 ? "f64" : "f32", LOG2N, LOG2E, inv ? "inv" : "fwd", e,
+               ok ? "ok" : "FAIL");
+        if (!ok) ++fails;
+    }
+}
+
+template <typename T, int LOG2N>
+void sizes(double tol) {
+    one<T, LOG2N, (LOG2N < 4 ? LOG2N : 4)>(tol);
+    if constexpr (LOG2N >= 3) one<T, LOG2N, 3>(tol);
+    if constexpr (LOG2N >= 2) one<T, LOG2N, 2>(tol);
+    if constexpr (LOG2N > 1) sizes<T, LOG2N - 1>(tol);
+}
+
+int main(int argc, char** argv) {
+    const int maxlog = 12;
+    (void)argc; (void)argv; (void)maxlog;
+    sizes<double, 12>(1e-14);
+    sizes<float, 11>(2e-6);
+    printf("fails=%d\n", fails);
+    return fails ? 1 : 0;
+}
