@@ -48,14 +48,19 @@ double check(bool inverse) {
             cx<T> r = regs[size_t(j) * E + Core::final_slot(e)];
             out[j + e * TPL] = inverse ? cswap(r) : r;
         }
-    // naive DFT in long double
+    // naive DFT in long double (cos/sin tabulated once per N)
     double num = 0, den = 0;
-    const double sgn = inverse ? 1.0 : -1.0;
+    std::vector<long double> ct(N), st(N);
+    for (int m = 0; m < N; ++m) {
+        long double a = 2.0L * M_PIl * m / N;
+        ct[m] = cosl(a);
+        st[m] = (inverse ? 1.0L : -1.0L) * sinl(a);
+    }
     for (int k = 0; k < N; ++k) {
         long double sr = 0, si = 0;
         for (int n = 0; n < N; ++n) {
-            long double a = sgn * 2.0L * M_PIl * ((long long)k * n % N) / N;
-            long double c = cosl(a), s = sinl(a);
+            const int idx = int((long long)k * n % N);
+            long double c = ct[idx], s = st[idx];
             sr += x[n].x * c - x[n].y * s;
             si += x[n].x * s + x[n].y * c;
         }

@@ -1,0 +1,75 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/dfft.h declares, and its host-only
+entry points (partition arithmetic, layouts, argument checking) agree with the oracle's restatement."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import distributedfft_b200 as dfft
+from distributedfft_b200 import _lib
+from oracle import dft_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "dfft.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dfft_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    names = declared_functions()
+    assert len(names) >= 40
+    raw = C.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in include/dfft.h but not exported by libdfft.so"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert _lib.lib().dfft_version() == 100
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libdfft.so")
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        _lib.lib()
+
+
+@pytest.mark.parametrize("n,parts", [(10, 4), (513, 4), (1024, 8), (7, 7), (129, 2)])
+def test_partition_matches_oracle(n, parts):
+    assert dfft.partition_sizes(n, parts) == O.split(n, parts)
+
+
+CASES = [
+    (dfft.SLAB_ZY_THEN_X, 64, 32, 16, 4, 1), (dfft.SLAB_ZY_THEN_X, 30, 20, 18, 8, 1), (dfft.SLAB_Z_THEN_YX, 64, 32, 16, 4, 1),
+    (dfft.SLAB_Z_THEN_YX, 17, 9, 30, 3, 1), (dfft.PENCIL, 64, 64, 64, 2, 4), (dfft.PENCIL, 64, 64, 64, 4, 2),
+    (dfft.PENCIL, 10, 12, 14, 3, 2), (dfft.PENCIL, 1024, 1024, 1024, 2, 4), (dfft.PENCIL, 8, 8, 8, 1, 1),
+]
+
+
+@pytest.mark.parametrize("decomp,nx,ny,nz,p1,p2", CASES)
+@pytest.mark.parametrize("transform", [dfft.R2C, dfft.C2C])
+def test_layouts_match_oracle_and_tile_the_domain(decomp, nx, ny, nz, p1, p2, transform):
+    P = p1 * p2
+    nzc = nz if transform == dfft.C2C else nz // 2 + 1
+    for which in range(4):
+        cover = 0
+        for r in range(P):
+            got = dfft.layout(decomp, transform, nx, ny, nz, p1, p2, r, which)
+            want = O.layout(decomp, transform, nx, ny, nz, p1, p2, r, which)
+            assert (list(got[0]), list(got[1])) == (list(want[0]), list(want[1])), (which, r)
+            cover += got[0][0] * got[0][1] * got[0][2]
+        assert cover == nx * ny * (nz if which == 0 else nzc)
+
+
+def test_argument_errors_have_codes_and_messages():
+    l = _lib.lib()
+    size = (C.c_size_t * 3)()
+    start = (C.c_size_t * 3)()
+    assert l.dfft_layout(dfft.PENCIL, dfft.R2C, 8, 8, 8, 2, 2, 7, 3, size, start) == -1
+    assert b"rank" in l.dfft_last_error_string()
+    assert l.dfft_layout(9, dfft.R2C, 8, 8, 8, 2, 2, 0, 3, size, start) == -1
+    assert l.dfft_partition(8, 0, size, start) == -1
+    with pytest.raises(_lib.DfftError):
+        _lib.check(l.dfft_exec_r2c(None, None, None))
