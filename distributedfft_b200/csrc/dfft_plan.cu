@@ -211,7 +211,7 @@ struct dfft_plan_s {
     std::vector<int> grp[3];
     int* err_d = nullptr;
     unsigned long long epoch = 0;
-    cudaStream_t own_stream = nullptr, last_stream = nullptr;
+    cudaStream_t own_stream = nullptr, last_stream = nullptr;  // last_stream: stream of the last exec
     Tables tabs;
     // schedules: [fwd/inv][d-1]
     Schedule sched[2][3];
@@ -234,37 +234,13 @@ static View single_view(void* base, long long sA0, long long sA1, long long sN) 
     View v{};
     v.seg_of_n = nullptr;
     v.nseg = 1;
+    v.sN = sN;
     v.seg[0].base = base;
     v.seg[0].sA0 = sA0;
     v.seg[0].sA1 = sA1;
-    v.seg[0].sN = sN;
     v.seg[0].n0 = 0;
     return v;
 }
-
-struct Builder {
-    dfft_plan_s* p;
-    const Geometry& g;
-    int me, i, j;
-    size_t es;
-    Builder(dfft_plan_s* p_) : p(p_), g(p_->g), me(p_->rank), i(p_->g.pi(p_->rank)), j(p_->g.pj(p_->rank)), es(p_->esize) {}
-
-    void* slot(int s, int r) const { return p->slot_ptr[s][r]; }
-
-    // slot assignment: D0, D1 direct targets of transposition 1 / 2; S, R NCCL staging
-    int slotD(int t) const { return t == 1 ? d0 : d1; }
-    int d0 = 0, d1 = 1, sS = 0, sR = 1;
-
-    Step pass(PassKind kind, size_t n, const char* phase) {
-        Step s;
-        s.type = STEP_PASS;
-        s.kind = kind;
-        s.log2n = ilog2_exact(n);
-        s.phase = phase;
-        s.prm.A0 = 1; s.prm.A1 = 1; s.prm.B = 1; s.prm.inverse = 0;
-        return s;
-    }
-};
 
 }  // namespace dfft
 
@@ -272,16 +248,6 @@ struct Builder {
 // Schedule construction
 // =====================================================================================================
 namespace dfft {
-
-// Describes one transposition for view construction.
-//   axis split on the producer side ("scatter", along the producer pass' transformed axis n) and on the
-//   consumer side ("gather", along the consumer pass' transformed axis).
-struct Trans {
-    int id;                  // 1 or 2 (which rendezvous group / config method)
-    bool direct;             // peer stores vs NCCL
-    std::vector<int> ranks;  // group members, index = position along the split
-    int mypos;
-};
 
 static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc);
 
@@ -293,19 +259,31 @@ static void plan_release_memory(dfft_plan_s* p);
 // -----------------------------------------------------------------------------------------------------
 namespace dfft {
 
-// Fill a segmented view over group members. f(q_pos, rank) returns {base, sA0, sA1, sN, n0}.
+// Fill a segmented view over group members. f(q_pos, rank) returns the segment and the (view-wide) stride
+// along the transformed axis.
+struct SegN {
+    Seg s;
+    long long sN;
+};
+static bool g_view_error = false;
 template <typename F>
 static void seg_view(View& v, const unsigned char* table, const std::vector<int>& ranks, F f) {
     v.seg_of_n = table;
     v.nseg = int(ranks.size());
-    for (size_t q = 0; q < ranks.size(); ++q) v.seg[q] = f(int(q), ranks[q]);
+    for (size_t q = 0; q < ranks.size(); ++q) {
+        SegN sn = f(int(q), ranks[q]);
+        v.seg[q] = sn.s;
+        if (q == 0) v.sN = sn.sN;
+        else if (v.sN != sn.sN) g_view_error = true;
+    }
     if (v.nseg == 1) v.seg_of_n = nullptr;
 }
 
-static Seg mkseg(void* base, long long sA0, long long sA1, long long sN, size_t n0) {
-    Seg s{};
-    s.base = base; s.sA0 = sA0; s.sA1 = sA1; s.sN = sN; s.n0 = int(n0);
-    return s;
+static SegN mkseg(void* base, long long sA0, long long sA1, long long sN, size_t n0) {
+    SegN r{};
+    r.s.base = base; r.s.sA0 = sA0; r.s.sA1 = sA1; r.s.n0 = int(n0);
+    r.sN = sN;
+    return r;
 }
 
 static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
@@ -851,6 +829,8 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
 }
 
 static int exec_common(dfft_plan_t p, void* out, const void* in, int inverse, int d, int need_transform, void* stream, bool sync) {
+    // sync == true: the plain calls run on the plan's own stream; _async calls use exactly the stream given
+    // (NULL = the CUDA default stream)
     if (!p) return fail(DFFT_ERR_INVALID, "null plan");
     if (!p->work) return fail(DFFT_ERR_STATE, "plan has no work area (call dfft_set_work_area)");
     if (p->g.transform != need_transform) return fail(DFFT_ERR_INVALID, need_transform == DFFT_C2C ? "plan was created for R2C/C2R" : "plan was created for C2C");
@@ -859,10 +839,12 @@ static int exec_common(dfft_plan_t p, void* out, const void* in, int inverse, in
     CK_CUDA(cudaSetDevice(p->comm->device));
     Schedule& sc = p->sched[inverse ? 1 : 0][d - 1];
     if (!sc.built) {
+        g_view_error = false;
         int rc = build_schedule(p, inverse ? 1 : 0, d, sc);
         if (rc) return rc;
+        if (g_view_error) return fail(DFFT_ERR_STATE, "internal: segments of one view disagree on the axis stride");
     }
-    cudaStream_t st = stream ? (cudaStream_t)stream : p->own_stream;
+    cudaStream_t st = sync ? p->own_stream : (cudaStream_t)stream;
     int rc = run_schedule(p, sc, out, in, st);
     if (rc) return rc;
     if (sync) return dfft_plan_wait(p);
@@ -1049,7 +1031,7 @@ int dfft_exec_c2c_async(dfft_plan_t p, void* out, const void* in, int direction,
 
 int dfft_plan_wait(dfft_plan_t p) {
     if (!p) return fail(DFFT_ERR_INVALID, "null plan");
-    CK_CUDA(cudaStreamSynchronize(p->last_stream ? p->last_stream : p->own_stream));
+    CK_CUDA(cudaStreamSynchronize(p->last_stream));
     int err = 0;
     CK_CUDA(cudaMemcpy(&err, p->err_d, sizeof(int), cudaMemcpyDeviceToHost));
     if (err) {

@@ -216,6 +216,25 @@ struct FftCore {
         return ((jb >> L2NS) << (L2NS + BITS)) + (jb & (NS - 1)) + q * NS;
     }
 
+    // scatter_pos(j, slot) == scatter_base(j) + scatter_off(slot): TPL is a multiple of Ns for every
+    // scattering stage, so the butterfly index b and output index q only add compile-time constants.
+    template <int ST>
+    static DFFT_HD int scatter_base(int j) {
+        constexpr int BITS = SP::bits(ST);
+        constexpr int L2NS = SP::log2ns(ST);
+        constexpr int NS = 1 << L2NS;
+        static_assert(TPL % NS == 0, "threads per line must be a multiple of Ns");
+        return ((j >> L2NS) << (L2NS + BITS)) + (j & (NS - 1));
+    }
+    template <int ST>
+    static DFFT_HDC int scatter_off(int slot) {
+        constexpr int BITS = SP::bits(ST);
+        constexpr int R = 1 << BITS;
+        constexpr int S = E / R;
+        constexpr int NS = 1 << SP::log2ns(ST);
+        return (slot % S) * TPL * R + bitrev_c(slot / S, BITS) * NS;
+    }
+
     // After the LAST stage, the value that belongs to output position j + e*TPL sits in slot
     // final_slot(e).
     static DFFT_HDC int final_slot(int e) {
@@ -227,8 +246,31 @@ struct FftCore {
     }
 };
 
-// Shared-memory padding for the contiguous-line layout: one extra element per 8 keeps the strided
-// first-stage scatter (thread stride R elements) conflict free for 16-byte elements.
+// ---------------------------------------------------------------------------------------------
+// Shared-memory layout of one CTA tile (N points x TB lines) between stages.
+//   CONTIG: idx(n, t) = t*NPAD + pad(n)      (lines side by side, threads walk along n)
+//   TILED:  idx(n, t) = pad(n)*TB + t        (threads walk along t; rows of TB elements)
+// pad(n) = n + (n >> SH) inserts one element (CONTIG) / one row (TILED) every 2^SH so that the strided
+// first-stage scatter is bank-conflict free; TILED rows of >= 128 bytes need no padding.
+// Both the scatter and the gather index split into a per-thread base plus a compile-time constant
+// (idx(base + off) = idx(base) + off_const) — see split_ok().
+// ---------------------------------------------------------------------------------------------
+template <int LOG2N, int LOG2E, int TB, bool TILED, int ELEM_BYTES>
+struct SmemLayout {
+    using SP = StagePlan<LOG2N, LOG2E>;
+    static constexpr int N = SP::N, TPL = SP::TPL;
+    static constexpr bool PAD = TILED ? (TB * ELEM_BYTES < 128) : true;
+    static constexpr int SH = TILED ? SP::bits(0) : (SP::bits(0) < 3 ? 3 : SP::bits(0));
+    static constexpr int NPAD = PAD ? N + (N >> SH) : N;
+    static constexpr int ELEMS = NPAD * TB;
+    static DFFT_HDC int pad(int n) { return PAD ? n + (n >> SH) : n; }
+    static DFFT_HDC int idx(int n, int t) { return TILED ? pad(n) * TB + t : t * NPAD + pad(n); }
+    // constant part contributed by an offset `off` added to n (valid when no carry crosses bit SH)
+    static DFFT_HDC int off(int o) { return TILED ? pad(o) * TB : pad(o); }
+    // gather positions j + e*TPL split when TPL is a multiple of the pad period
+    static constexpr bool GATHER_SPLIT = !PAD || (TPL % (1 << SH) == 0);
+};
+
 DFFT_HDC int pad_idx(int i) { return i + (i >> 3); }
 DFFT_HDC int padded_len(int n) { return n + (n >> 3); }
 

@@ -24,23 +24,28 @@ cudaError_t launch_pass(PassKind kind, const FftParams& p, cudaStream_t stream) 
     switch (kind) {
         case PASS_C2C_CONTIG: {
             using C = CtaFft<T, LOG2N, LOG2E, S::TBC, false>;
-            auto k = fft_c2c_kernel<T, LOG2N, LOG2E, S::TBC, false>;
-            static cudaError_t once = set_smem(k, C::SMEM_BYTES);
+            auto kf = fft_c2c_kernel<T, LOG2N, LOG2E, S::TBC, false, false>;
+            auto ki = fft_c2c_kernel<T, LOG2N, LOG2E, S::TBC, false, true>;
+            static cudaError_t once = set_smem(kf, C::SMEM_BYTES) != cudaSuccess ? cudaErrorInvalidValue : set_smem(ki, C::SMEM_BYTES);
             if (once != cudaSuccess) return once;
+            if (p.in.sN != 1 || p.out.sN != 1) return cudaErrorInvalidValue;
             const long long grid = (lines + S::TBC - 1) / S::TBC;
             if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-            k<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
+            if (p.inverse) ki<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
+            else kf<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
             break;
         }
         case PASS_C2C_TILED: {
             using C = CtaFft<T, LOG2N, LOG2E, S::TBT, true>;
-            auto k = fft_c2c_kernel<T, LOG2N, LOG2E, S::TBT, true>;
-            static cudaError_t once = set_smem(k, C::SMEM_BYTES);
+            auto kf = fft_c2c_kernel<T, LOG2N, LOG2E, S::TBT, true, false>;
+            auto ki = fft_c2c_kernel<T, LOG2N, LOG2E, S::TBT, true, true>;
+            static cudaError_t once = set_smem(kf, C::SMEM_BYTES) != cudaSuccess ? cudaErrorInvalidValue : set_smem(ki, C::SMEM_BYTES);
             if (once != cudaSuccess) return once;
             if (p.B <= 0) return cudaSuccess;
             const long long grid = lines * ((p.B + S::TBT - 1) / S::TBT);
             if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-            k<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
+            if (p.inverse) ki<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
+            else kf<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
             break;
         }
         case PASS_R2C: {
@@ -48,6 +53,7 @@ cudaError_t launch_pass(PassKind kind, const FftParams& p, cudaStream_t stream) 
             auto k = fft_r2c_kernel<T, LOG2N, LOG2E, S::TBC>;
             static cudaError_t once = set_smem(k, C::SMEM_BYTES);
             if (once != cudaSuccess) return once;
+            if (p.in.nseg != 1 || p.in.sN != 1 || p.out.sN != 1) return cudaErrorInvalidValue;
             const long long grid = (lines + S::TBC - 1) / S::TBC;
             if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
             k<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
@@ -58,6 +64,7 @@ cudaError_t launch_pass(PassKind kind, const FftParams& p, cudaStream_t stream) 
             auto k = fft_c2r_kernel<T, LOG2N, LOG2E, S::TBC>;
             static cudaError_t once = set_smem(k, C::SMEM_BYTES);
             if (once != cudaSuccess) return once;
+            if (p.out.nseg != 1 || p.in.sN != 1 || p.out.sN != 1) return cudaErrorInvalidValue;
             const long long grid = (lines + S::TBC - 1) / S::TBC;
             if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
             k<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);

@@ -15,6 +15,11 @@
 //            every global access is a TB*sizeof(complex) byte run.
 // Both stage through shared memory between radix stages only; first-stage loads and last-stage stores
 // go registers <-> HBM directly (one read + one write of the array per pass = the algorithmic minimum).
+//
+// Instruction diet (the kernels are close to issue-bound in fp64): direction is a template parameter,
+// single-segment views use one base pointer plus immediate / incremental offsets, multi-segment views
+// read a per-line table of segment bases from shared memory, and shared-memory indices are a
+// per-thread base plus compile-time constants (SmemLayout in fft_core.cuh).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -25,16 +30,17 @@ namespace dfft {
 constexpr int MAXSEG = 16;
 
 struct Seg {
-    void* base;        // element pointer (complex elements of the pass' precision)
-    long long sA0;     // stride of batch index a0 (elements)
-    long long sA1;     // stride of batch index a1
-    long long sN;      // stride along the transformed axis
-    int n0;            // first n covered by this segment
+    void* base;     // element pointer (complex elements of the pass' precision)
+    long long sA0;  // stride of batch index a0 (elements)
+    long long sA1;  // stride of batch index a1
+    int n0;         // first n covered by this segment
     int pad_;
 };
 
+// element (a0, a1, n, b) of segment s lives at  seg[s].base + a0*sA0 + a1*sA1 + (n - n0)*sN + b
 struct View {
     const unsigned char* seg_of_n;  // n -> segment id (device memory); ignored when nseg == 1
+    long long sN;                   // stride along the transformed axis (same for every segment)
     int nseg;
     int pad_;
     Seg seg[MAXSEG];
@@ -42,11 +48,11 @@ struct View {
 
 struct FftParams {
     View in, out;
-    int A0, A1;        // batch extents: line id = a0*A1 + a1
-    int B;             // TILED: extent of the contiguous dimension; CONTIG: 1
-    int inverse;       // 0 forward (e^-), 1 inverse (e^+), both unnormalised like cuFFT
-    const void* tw;    // exp(-2*pi*i*m/N), m < N, N = pass length (complex length for R2C/C2R)
-    const void* tw2;   // R2C/C2R only: exp(-2*pi*i*k/(2N)), k <= N/2
+    int A0, A1;       // batch extents: line id = a0*A1 + a1
+    int B;            // TILED: extent of the contiguous dimension; CONTIG: 1
+    int inverse;      // 0 forward (e^-), 1 inverse (e^+), both unnormalised like cuFFT
+    const void* tw;   // exp(-2*pi*i*m/N), m < N, N = pass length (complex length for R2C/C2R)
+    const void* tw2;  // R2C/C2R only: exp(-2*pi*i*k/(2N)), k <= N/2
 };
 
 enum PassKind { PASS_C2C_CONTIG = 0, PASS_C2C_TILED = 1, PASS_R2C = 2, PASS_C2R = 3 };
@@ -70,18 +76,6 @@ struct Shape {
     static constexpr int TBT = TBT_ > CAP ? (CAP < 1 ? 1 : CAP) : TBT_;
 };
 
-// ---- addressing ------------------------------------------------------------------------------------
-template <typename T>
-struct Addr {
-    // pointer to element (a0,a1,n,b) of a view
-    static __device__ __forceinline__ cx<T>* at(const View& v, int a0, int a1, int n, int b) {
-        int s = 0;
-        if (v.nseg > 1) s = v.seg_of_n[n];
-        const Seg& g = v.seg[s];
-        return reinterpret_cast<cx<T>*>(g.base) + (a0 * g.sA0 + a1 * g.sA1 + (long long)(n - g.n0) * g.sN + b);
-    }
-};
-
 template <typename T>
 __device__ __forceinline__ cx<T> ld_elem(const cx<T>* p) {
     if constexpr (sizeof(T) == 8) {
@@ -98,27 +92,55 @@ __device__ __forceinline__ void st_elem(cx<T>* p, cx<T> v) {
     else *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y);
 }
 
+// ---- per-thread access to one line of a view ----------------------------------------------------------
+// LINES = lines per CTA that need their own segment table (TB for CONTIG, 1 for TILED).
+template <typename T, int LINES>
+struct LineAccess {
+    static constexpr int TABLE_ELEMS = LINES * MAXSEG;  // unsigned long long entries in shared memory
+    const View& v;
+    cx<T>* p0;                  // single segment: element n = 0 of this thread's line (b included)
+    const unsigned long long* tab;  // multi segment: tab[s] = address of element n = 0 of segment s (b excluded)
+    long long boff;             // multi segment: + b (elements)
+    bool multi;
+
+    // fills the shared-memory table (all threads of the CTA call this; a __syncthreads follows outside)
+    static __device__ __forceinline__ void fill_table(const View& v, unsigned long long* table, int line_in_cta, int lane_in_line,
+                                                      int lanes_per_line, int a0, int a1) {
+        if (v.nseg <= 1) return;
+        for (int s = lane_in_line; s < v.nseg; s += lanes_per_line) {
+            const Seg& g = v.seg[s];
+            cx<T>* p = reinterpret_cast<cx<T>*>(g.base) + (a0 * g.sA0 + a1 * g.sA1 - (long long)g.n0 * v.sN);
+            table[line_in_cta * MAXSEG + s] = reinterpret_cast<unsigned long long>(p);
+        }
+    }
+    __device__ __forceinline__ LineAccess(const View& v_, const unsigned long long* table, int line_in_cta, int a0, int a1, int b)
+        : v(v_) {
+        multi = v.nseg > 1;
+        const Seg& g = v.seg[0];
+        p0 = reinterpret_cast<cx<T>*>(g.base) + (a0 * g.sA0 + a1 * g.sA1 - (long long)g.n0 * v.sN + b);
+        tab = table + line_in_cta * MAXSEG;
+        boff = b;
+    }
+    __device__ __forceinline__ cx<T>* at(int n) const {
+        if (!multi) return p0 + (long long)n * v.sN;
+        const int s = v.seg_of_n[n];
+        return reinterpret_cast<cx<T>*>(tab[s]) + ((long long)n * v.sN + boff);
+    }
+};
+
 // ---- the in-CTA transform ---------------------------------------------------------------------------
 template <typename T, int LOG2N, int LOG2E, int TB, bool TILED>
 struct CtaFft {
     using Core = FftCore<T, LOG2N, LOG2E>;
+    using L = SmemLayout<LOG2N, LOG2E, TB, TILED, int(sizeof(cx<T>))>;
     static constexpr int N = Core::N, E = Core::E, TPL = Core::TPL, NST = Core::NST;
     static constexpr int THREADS = TPL * TB;
-    static constexpr int ROWB = TB * int(sizeof(cx<T>));
-    static constexpr int PADSH = StagePlan<LOG2N, LOG2E>::bits(0) < 3 ? 3 : StagePlan<LOG2N, LOG2E>::bits(0);
-    static constexpr bool PAD = TILED ? (ROWB < 128) : true;
-    static constexpr int PADSH_T = StagePlan<LOG2N, LOG2E>::bits(0);
-    static constexpr int NPAD = TILED ? (PAD ? N + (N >> PADSH_T) : N) : (N + (N >> PADSH));
-    static constexpr size_t SMEM_BYTES = (NST > 1 || true) ? size_t(NPAD) * TB * sizeof(cx<T>) : 0;
+    static constexpr int LINES = TILED ? 1 : TB;
+    static constexpr size_t TILE_BYTES = size_t(L::ELEMS) * sizeof(cx<T>);
+    static constexpr size_t TABLE_BYTES = size_t(2) * LINES * MAXSEG * sizeof(unsigned long long);
+    static constexpr size_t SMEM_BYTES = TILE_BYTES + TABLE_BYTES;
 
-    static __device__ __forceinline__ int sidx(int n, int t) {
-        if constexpr (TILED) {
-            if constexpr (PAD) return (n + (n >> PADSH_T)) * TB + t;
-            else return n * TB + t;
-        } else {
-            return t * NPAD + n + (n >> PADSH);
-        }
-    }
+    static __device__ __forceinline__ int sidx(int n, int t) { return L::idx(n, t); }
 
     // synchronise the threads that cooperate on one line (CONTIG) or the whole tile (TILED)
     static __device__ __forceinline__ void sync(int t) {
@@ -133,59 +155,109 @@ struct CtaFft {
         }
     }
 
+    // gather: v[e] = tile[j + e*TPL]
+    static __device__ __forceinline__ void gather(cx<T> (&v)[E], const cx<T>* sm, int j, int t) {
+        if constexpr (L::GATHER_SPLIT) {
+            const cx<T>* p = sm + L::idx(j, t);
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = p[L::off(e * TPL)];
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = sm[L::idx(j + e * TPL, t)];
+        }
+    }
+
     template <int ST>
     static __device__ __forceinline__ void stages(cx<T> (&v)[E], int j, int t, cx<T>* sm, const cx<T>* tw) {
         Core::template stage_compute<ST>(v, j, tw);
         if constexpr (ST + 1 < NST) {
             if constexpr (ST > 0) sync(t);
+            cx<T>* p = sm + L::idx(Core::template scatter_base<ST>(j), t);
 #pragma unroll
-            for (int e = 0; e < E; ++e) sm[sidx(Core::template scatter_pos<ST>(j, e), t)] = v[e];
+            for (int e = 0; e < E; ++e) p[L::off(Core::template scatter_off<ST>(e))] = v[e];
             sync(t);
-#pragma unroll
-            for (int e = 0; e < E; ++e) v[e] = sm[sidx(j + e * TPL, t)];
+            gather(v, sm, j, t);
             stages<ST + 1>(v, j, t, sm, tw);
         }
     }
 };
 
+// common prologue: thread -> (j, t), tile -> (a0, a1, b), segment tables
+template <typename C, bool TILED, int TB>
+struct TileCoord {
+    int j, t, a0, a1, b;
+    bool valid;
+    __device__ __forceinline__ TileCoord(const FftParams& p) {
+        const int tid = threadIdx.x;
+        if constexpr (TILED) { t = tid % TB; j = tid / TB; }
+        else { j = tid % C::TPL; t = tid / C::TPL; }
+        if constexpr (TILED) {
+            const int nbt = (p.B + TB - 1) / TB;
+            const int bt = blockIdx.x % nbt;
+            const int a = blockIdx.x / nbt;
+            b = bt * TB + t;
+            valid = b < p.B;
+            a1 = a % p.A1;
+            a0 = a / p.A1;
+        } else {
+            const long long line = (long long)blockIdx.x * TB + t;
+            valid = line < (long long)p.A0 * p.A1;
+            a1 = int(line % p.A1);
+            a0 = int(line / p.A1);
+            b = 0;
+        }
+    }
+};
+
 // ---- C2C pass ------------------------------------------------------------------------------------------
-template <typename T, int LOG2N, int LOG2E, int TB, bool TILED>
+template <typename T, int LOG2N, int LOG2E, int TB, bool TILED, bool INV>
 __global__ void __launch_bounds__((1 << (LOG2N - LOG2E)) * TB)
 fft_c2c_kernel(const __grid_constant__ FftParams p) {
     using C = CtaFft<T, LOG2N, LOG2E, TB, TILED>;
+    using LA = LineAccess<T, C::LINES>;
     constexpr int E = C::E, TPL = C::TPL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
+    unsigned long long* tab_in = reinterpret_cast<unsigned long long*>(smem_raw + C::TILE_BYTES);
+    unsigned long long* tab_out = tab_in + C::LINES * MAXSEG;
 
-    const int tid = threadIdx.x;
-    int j, t;
-    if constexpr (TILED) { t = tid % TB; j = tid / TB; }
-    else { j = tid % TPL; t = tid / TPL; }
-
-    int a0, a1, b;
-    bool valid;
-    if constexpr (TILED) {
-        const int nbt = (p.B + TB - 1) / TB;
-        const int bt = blockIdx.x % nbt;
-        const int a = blockIdx.x / nbt;
-        b = bt * TB + t;
-        valid = b < p.B;
-        a1 = a % p.A1;
-        a0 = a / p.A1;
-    } else {
-        const long long line = (long long)blockIdx.x * TB + t;
-        valid = line < (long long)p.A0 * p.A1;
-        a1 = int(line % p.A1);
-        a0 = int(line / p.A1);
-        b = 0;
+    const TileCoord<C, TILED, TB> tc(p);
+    const int j = tc.j, t = tc.t;
+    const bool multi = p.in.nseg > 1 || p.out.nseg > 1;
+    if (multi) {
+        // TILED: one table per CTA (a0, a1 are CTA-uniform), filled by the first threads;
+        // CONTIG: one table per line, filled by that line's threads.
+        const int line = TILED ? 0 : t;
+        const int lane = TILED ? int(threadIdx.x) : j;
+        const int lanes = TILED ? C::THREADS : TPL;
+        LA::fill_table(p.in, tab_in, line, lane, lanes, tc.a0, tc.a1);
+        LA::fill_table(p.out, tab_out, line, lane, lanes, tc.a0, tc.a1);
+        __syncthreads();
     }
+    const LA in(p.in, tab_in, TILED ? 0 : t, tc.a0, tc.a1, tc.b);
+    const LA out(p.out, tab_out, TILED ? 0 : t, tc.a0, tc.a1, tc.b);
 
     cx<T> v[E];
-    if (valid) {
+    if (tc.valid) {
+        if (!in.multi) {
+            if constexpr (!TILED) {
+                // contiguous line: sN == 1, immediate offsets
+                const cx<T>* q = in.p0 + j;
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            cx<T> x = ld_elem<T>(Addr<T>::at(p.in, a0, a1, j + e * TPL, b));
-            v[e] = p.inverse ? cswap(x) : x;
+                for (int e = 0; e < E; ++e) v[e] = ld_elem<T>(q + e * TPL);
+            } else {
+                const long long step = (long long)TPL * p.in.sN;
+                const cx<T>* q = in.p0 + (long long)j * p.in.sN;
+#pragma unroll
+                for (int e = 0; e < E; ++e) { v[e] = ld_elem<T>(q); q += step; }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = ld_elem<T>(in.at(j + e * TPL));
+        }
+        if constexpr (INV) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = cswap(v[e]);
         }
     } else {
 #pragma unroll
@@ -194,11 +266,31 @@ fft_c2c_kernel(const __grid_constant__ FftParams p) {
 
     C::template stages<0>(v, j, t, sm, reinterpret_cast<const cx<T>*>(p.tw));
 
-    if (valid) {
+    if (tc.valid) {
+        if (!out.multi) {
+            if constexpr (!TILED) {
+                cx<T>* q = out.p0 + j;
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            cx<T> x = v[C::Core::final_slot(e)];
-            st_elem<T>(Addr<T>::at(p.out, a0, a1, j + e * TPL, b), p.inverse ? cswap(x) : x);
+                for (int e = 0; e < E; ++e) {
+                    const cx<T> x = v[C::Core::final_slot(e)];
+                    st_elem<T>(q + e * TPL, INV ? cswap(x) : x);
+                }
+            } else {
+                const long long step = (long long)TPL * p.out.sN;
+                cx<T>* q = out.p0 + (long long)j * p.out.sN;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const cx<T> x = v[C::Core::final_slot(e)];
+                    st_elem<T>(q, INV ? cswap(x) : x);
+                    q += step;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const cx<T> x = v[C::Core::final_slot(e)];
+                st_elem<T>(out.at(j + e * TPL), INV ? cswap(x) : x);
+            }
         }
     }
 }
@@ -210,19 +302,27 @@ template <typename T, int LOG2M, int LOG2E, int TB>
 __global__ void __launch_bounds__((1 << (LOG2M - LOG2E)) * TB)
 fft_r2c_kernel(const __grid_constant__ FftParams p) {
     using C = CtaFft<T, LOG2M, LOG2E, TB, false>;
+    using LA = LineAccess<T, C::LINES>;
     constexpr int E = C::E, TPL = C::TPL, M = C::N, NST = C::NST;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int j = tid % TPL, t = tid / TPL;
-    const long long line = (long long)blockIdx.x * TB + t;
-    const bool valid = line < (long long)p.A0 * p.A1;
-    const int a1 = int(line % p.A1), a0 = int(line / p.A1);
+    unsigned long long* tab_in = reinterpret_cast<unsigned long long*>(smem_raw + C::TILE_BYTES);
+    unsigned long long* tab_out = tab_in + C::LINES * MAXSEG;
+    const TileCoord<C, false, TB> tc(p);
+    const int j = tc.j, t = tc.t;
+    const bool valid = tc.valid;
+    if (p.out.nseg > 1) {
+        LA::fill_table(p.out, tab_out, t, j, TPL, tc.a0, tc.a1);
+        __syncthreads();
+    }
+    const LA in(p.in, tab_in, t, tc.a0, tc.a1, 0);
+    const LA out(p.out, tab_out, t, tc.a0, tc.a1, 0);
 
     cx<T> v[E];
     if (valid) {
+        const cx<T>* q = in.p0 + j;
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = ld_elem<T>(Addr<T>::at(p.in, a0, a1, j + e * TPL, 0));
+        for (int e = 0; e < E; ++e) v[e] = ld_elem<T>(q + e * TPL);
     } else {
 #pragma unroll
         for (int e = 0; e < E; ++e) v[e] = cx<T>{T(0), T(0)};
@@ -244,17 +344,13 @@ fft_r2c_kernel(const __grid_constant__ FftParams p) {
         const cx<T> xo = cx<T>{T(0.5) * d.y, T(-0.5) * d.x};  // -i/2 * d
         const cx<T> tt = cmul(ld_tw(tw2, k), xo);
         if (valid) {
-            st_elem<T>(Addr<T>::at(p.out, a0, a1, k, 0), cadd(xe, tt));
-            st_elem<T>(Addr<T>::at(p.out, a0, a1, M - k, 0), cconj(csub(xe, tt)));
+            st_elem<T>(out.at(k), cadd(xe, tt));
+            st_elem<T>(out.at(M - k), cconj(csub(xe, tt)));
         }
     };
-    if constexpr (E >= 2) {
 #pragma unroll
-        for (int e = 0; e < E / 2; ++e) emit(j + e * TPL);
-        if (j == 0) emit(M / 2);
-    } else {
-        emit(0);
-    }
+    for (int e = 0; e < E / 2; ++e) emit(j + e * TPL);
+    if (j == 0) emit(M / 2);
 }
 
 // ---- C2R pass (CONTIG): M+1 complex points -> real line of 2M points, unnormalised -----------------------
@@ -262,22 +358,29 @@ template <typename T, int LOG2M, int LOG2E, int TB>
 __global__ void __launch_bounds__((1 << (LOG2M - LOG2E)) * TB)
 fft_c2r_kernel(const __grid_constant__ FftParams p) {
     using C = CtaFft<T, LOG2M, LOG2E, TB, false>;
+    using LA = LineAccess<T, C::LINES>;
     constexpr int E = C::E, TPL = C::TPL, M = C::N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int j = tid % TPL, t = tid / TPL;
-    const long long line = (long long)blockIdx.x * TB + t;
-    const bool valid = line < (long long)p.A0 * p.A1;
-    const int a1 = int(line % p.A1), a0 = int(line / p.A1);
+    unsigned long long* tab_in = reinterpret_cast<unsigned long long*>(smem_raw + C::TILE_BYTES);
+    unsigned long long* tab_out = tab_in + C::LINES * MAXSEG;
+    const TileCoord<C, false, TB> tc(p);
+    const int j = tc.j, t = tc.t;
+    const bool valid = tc.valid;
+    if (p.in.nseg > 1) {
+        LA::fill_table(p.in, tab_in, t, j, TPL, tc.a0, tc.a1);
+        __syncthreads();
+    }
+    const LA in(p.in, tab_in, t, tc.a0, tc.a1, 0);
+    const LA out(p.out, tab_out, t, tc.a0, tc.a1, 0);
 
     const cx<T>* tw2 = reinterpret_cast<const cx<T>*>(p.tw2);
     // Z[k] = (X[k] + conj X[M-k]) + i * conj(W^k) * (X[k] - conj X[M-k]);  Z[M-k] = conj(Xe' - i Xo')
     auto build = [&](int k) {
         cx<T> xk{T(0), T(0)}, xm{T(0), T(0)};
         if (valid) {
-            xk = ld_elem<T>(Addr<T>::at(p.in, a0, a1, k, 0));
-            xm = cconj(ld_elem<T>(Addr<T>::at(p.in, a0, a1, M - k, 0)));
+            xk = ld_elem<T>(in.at(k));
+            xm = cconj(ld_elem<T>(in.at(M - k)));
         }
         const cx<T> xe = cadd(xk, xm);
         const cx<T> xo = cmul(cconj(ld_tw(tw2, k)), csub(xk, xm));
@@ -285,23 +388,18 @@ fft_c2r_kernel(const __grid_constant__ FftParams p) {
         sm[C::sidx(k, t)] = cswap(cx<T>{xe.x - xo.y, xe.y + xo.x});
         if (k != 0) sm[C::sidx(M - k, t)] = cswap(cx<T>{xe.x + xo.y, -(xe.y - xo.x)});
     };
-    if constexpr (E >= 2) {
 #pragma unroll
-        for (int e = 0; e < E / 2; ++e) build(j + e * TPL);
-        if (j == 0) build(M / 2);
-    } else {
-        build(0);
-    }
+    for (int e = 0; e < E / 2; ++e) build(j + e * TPL);
+    if (j == 0) build(M / 2);
     C::sync(t);
     cx<T> v[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = sm[C::sidx(j + e * TPL, t)];
+    C::gather(v, sm, j, t);
     if constexpr (C::NST > 1) C::sync(t);
     C::template stages<0>(v, j, t, sm, reinterpret_cast<const cx<T>*>(p.tw));
     if (valid) {
+        cx<T>* q = out.p0 + j;
 #pragma unroll
-        for (int e = 0; e < E; ++e)
-            st_elem<T>(Addr<T>::at(p.out, a0, a1, j + e * TPL, 0), cswap(v[C::Core::final_slot(e)]));
+        for (int e = 0; e < E; ++e) st_elem<T>(q + e * TPL, cswap(v[C::Core::final_slot(e)]));
     }
 }
 

@@ -214,12 +214,27 @@ class MPIcuFFT_Pencil(MPIcuFFT):
     """z FFT -> transpose -> y FFT -> transpose -> x FFT on a P1 x P2 grid. include/mpicufft_pencil.hpp."""
     _decomp = PENCIL
 
+    def initFFT(self, global_size, partition=None, allocate=True):
+        if partition is None or global_size is None:
+            raise RuntimeError("GlobalSize or Partition not initialized!")
+        if partition.P1 * partition.P2 != self.comm.size:
+            raise RuntimeError("Invalid Input Partition!")
+        self.partition = partition
+        super().initFFT(global_size, partition, allocate)
+
     def getPartitionDimensions(self):
-        """(input_dim, transposed_dim, output_dim) as dicts of size/start lists (mpicufft_pencil.hpp:112-116)."""
+        """(input_dim, transposed_dim, output_dim), each a dict with size_x/y/z and start_x/y/z lists
+        (Partition_Dimensions, params.hpp:58-81; mpicufft_pencil.hpp:112-116)."""
         from .params import partition_sizes
-        g = self.global_size
-        p1 = self.comm.size if False else None  # placeholder to keep signature simple
-        raise NotImplementedError("use layout() for per-rank geometry")
+        g, p = self.global_size, self.partition
+        nzc = g.Nz if self.transform == C2C else g.Nz // 2 + 1
+
+        def dims(nx_parts, ny_parts, nz_parts, nz):
+            d = {}
+            for ax, n, parts in (("x", g.Nx, nx_parts), ("y", g.Ny, ny_parts), ("z", nz, nz_parts)):
+                d[f"size_{ax}"], d[f"start_{ax}"] = partition_sizes(n, parts)
+            return d
+        return dims(p.P1, p.P2, 1, g.Nz), dims(p.P1, 1, p.P2, nzc), dims(1, p.P1, p.P2, nzc)
 
 
 def layout(decomp: int, transform: int, nx: int, ny: int, nz: int, p1: int, p2: int, rank: int, which: int):

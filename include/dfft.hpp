@@ -1,0 +1,168 @@
+// dfft.hpp — header-only C++ shim that re-creates the reference's class and method names
+// (/root/reference/include/mpicufft.hpp:55-105, mpicufft_slab.hpp:88-125, mpicufft_slab_z_then_yx.hpp,
+// mpicufft_pencil.hpp:71-122, params.hpp:24-93) on top of the C ABI in dfft.h, so that caller code
+// written against eggersn/DistributedFFT compiles with `MPI_Comm` replaced by `dfft_comm_t`:
+//
+//     Configurations config{true, 0, Peer2Peer, Sync, "", Peer2Peer, Sync};
+//     MPIcuFFT_Slab<double> fft(config, comm);
+//     GlobalSize gs(Nx, Ny, Nz);
+//     fft.initFFT(&gs, true);
+//     fft.execR2C(out_d, in_d);
+//
+// Error convention follows the reference: failures print the message and exit(EXIT_FAILURE)
+// (/root/reference/src/slab/default/mpicufft_slab.cpp:23-29); the pencil class throws
+// std::runtime_error for an uninitialised plan (/root/reference/src/pencil/mpicufft_pencil.cpp:22-25).
+#pragma once
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "dfft.h"
+
+struct GlobalSize {
+    GlobalSize(size_t Nx_, size_t Ny_, size_t Nz_) : Nx(Nx_), Ny(Ny_), Nz(Nz_), Nz_out(Nz_ / 2 + 1) {}
+    size_t Nx, Ny, Nz, Nz_out;
+};
+struct Partition { size_t P1, P2; };
+struct Slab_Partition : public Partition { explicit Slab_Partition(size_t P1_) { P1 = P1_; P2 = 1; } };
+struct Pencil_Partition : public Partition { Pencil_Partition(size_t P1_, size_t P2_) { P1 = P1_; P2 = P2_; } };
+
+struct Partition_Dimensions {
+    std::vector<size_t> size_x, size_y, size_z, start_x, start_y, start_z;
+};
+
+enum CommunicationMethod { Peer2Peer, All2All };
+enum SendMethod { Sync, Streams, MPI_Type };
+struct Configurations {
+    bool cuda_aware;
+    int warmup_rounds;
+    CommunicationMethod comm_method;
+    SendMethod send_method;
+    std::string benchmark_dir;
+    CommunicationMethod comm_method2;
+    SendMethod send_method2;
+};
+
+namespace dfft_shim {
+template <typename T> struct prec;
+template <> struct prec<float> { static constexpr int value = DFFT_F32; };
+template <> struct prec<double> { static constexpr int value = DFFT_F64; };
+inline void die(int rc, const char* file, int line) {
+    if (rc < 0) {
+        std::printf("Error %d at %s:%d: %s\n", rc, file, line, dfft_last_error_string());
+        std::exit(EXIT_FAILURE);
+    }
+}
+}  // namespace dfft_shim
+#define DFFT_CALL(x) dfft_shim::die((x), __FILE__, __LINE__)
+
+template <typename T>
+class MPIcuFFT {
+public:
+    MPIcuFFT(Configurations config_, dfft_comm_t comm_, int /*max_world_size*/ = -1, int transform_ = DFFT_R2C)
+        : config(config_), comm(comm_), transform(transform_) {
+        pidx = dfft_comm_rank(comm);
+        pcnt = dfft_comm_size(comm);
+    }
+    virtual ~MPIcuFFT() { if (plan) dfft_plan_destroy(plan); }
+
+    virtual void initFFT(GlobalSize* global_size, Partition* partition, bool allocate = true) = 0;
+    virtual void setWorkArea(void* device = nullptr, void* host = nullptr) { DFFT_CALL(dfft_set_work_area(plan, device, host)); }
+    virtual void execR2C(void* out, const void* in) = 0;
+
+    virtual void getInSize(size_t* isize) { DFFT_CALL(dfft_get_in_size(plan, isize)); }
+    virtual void getInStart(size_t* istart) { DFFT_CALL(dfft_get_in_start(plan, istart)); }
+    virtual void getOutSize(size_t* osize) { DFFT_CALL(dfft_get_out_size(plan, osize)); }
+    virtual void getOutStart(size_t* ostart) { DFFT_CALL(dfft_get_out_start(plan, ostart)); }
+
+    size_t getDomainSize() const { return dfft_get_domain_size(plan); }
+    size_t getWorkSizeDevice() const { return dfft_get_work_size_device(plan); }
+    size_t getWorkSizeHost() const { return dfft_get_work_size_host(plan); }
+    void* getWorkAreaDevice() const { return dfft_get_work_area_device(plan); }
+    void* getWorkAreaHost() const { return nullptr; }
+    int getRank() const { return pidx; }
+    int getWorldSize() const { return pcnt; }
+    dfft_plan_t handle() const { return plan; }
+
+protected:
+    void create(int decomp, GlobalSize* gs, size_t p1, size_t p2, bool allocate) {
+        dfft_config c{};
+        c.cuda_aware = config.cuda_aware; c.warmup_rounds = config.warmup_rounds;
+        c.comm_method = config.comm_method; c.send_method = config.send_method;
+        c.benchmark_dir = config.benchmark_dir.empty() ? nullptr : config.benchmark_dir.c_str();
+        c.comm_method2 = config.comm_method2; c.send_method2 = config.send_method2;
+        if (plan) { dfft_plan_destroy(plan); plan = nullptr; }
+        DFFT_CALL(dfft_plan_create(comm, &c, decomp, dfft_shim::prec<T>::value, transform, gs->Nx, gs->Ny, gs->Nz, p1, p2, allocate ? 1 : 0, &plan));
+        initialized = true;
+    }
+    Configurations config;
+    dfft_comm_t comm;
+    int transform;
+    int pidx = 0, pcnt = 1;
+    dfft_plan_t plan = nullptr;
+    bool initialized = false;
+};
+
+template <typename T>
+class MPIcuFFT_Slab : public MPIcuFFT<T> {
+public:
+    using MPIcuFFT<T>::MPIcuFFT;
+    void initFFT(GlobalSize* global_size, Partition* /*partition*/, bool allocate = true) override {
+        this->create(DFFT_SLAB_ZY_THEN_X, global_size, size_t(this->pcnt), 1, allocate);
+    }
+    void initFFT(GlobalSize* global_size, bool allocate = true) { initFFT(global_size, nullptr, allocate); }
+    void execR2C(void* out, const void* in) override { if (!this->initialized) return; DFFT_CALL(dfft_exec_r2c(this->plan, out, in)); }
+    virtual void execC2R(void* out, const void* in) { if (!this->initialized) return; DFFT_CALL(dfft_exec_c2r(this->plan, out, in)); }
+    // not in the reference: complex transform (plan constructed with transform_ = DFFT_C2C)
+    virtual void execC2C(void* out, const void* in, int direction) { DFFT_CALL(dfft_exec_c2c(this->plan, out, in, direction)); }
+};
+
+template <typename T>
+class MPIcuFFT_Slab_Z_Then_YX : public MPIcuFFT_Slab<T> {
+public:
+    using MPIcuFFT_Slab<T>::MPIcuFFT_Slab;
+    void initFFT(GlobalSize* global_size, Partition* /*partition*/, bool allocate = true) override {
+        this->create(DFFT_SLAB_Z_THEN_YX, global_size, size_t(this->pcnt), 1, allocate);
+    }
+};
+
+template <typename T>
+class MPIcuFFT_Pencil : public MPIcuFFT<T> {
+public:
+    using MPIcuFFT<T>::MPIcuFFT;
+    void initFFT(GlobalSize* global_size, Partition* partition, bool allocate = true) override {
+        if (partition == nullptr || global_size == nullptr) throw std::runtime_error("GlobalSize or Partition not initialized!");
+        if (partition->P1 * partition->P2 != size_t(this->pcnt)) throw std::runtime_error("Invalid Input Partition!");
+        gs_ = *global_size; part_ = *partition;
+        this->create(DFFT_PENCIL, global_size, partition->P1, partition->P2, allocate);
+    }
+    void execR2C(void* out, const void* in) override { execR2C(out, in, 3); }
+    virtual void execC2R(void* out, const void* in) { execC2R(out, in, 3); }
+    virtual void execR2C(void* out, const void* in, int d) {
+        if (!this->initialized) throw std::runtime_error("cuFFT plans are not yet initialized!");
+        DFFT_CALL(dfft_exec_r2c_partial(this->plan, out, in, d));
+    }
+    virtual void execC2R(void* out, const void* in, int d) {
+        if (!this->initialized) throw std::runtime_error("cuFFT plans are not yet initialized!");
+        DFFT_CALL(dfft_exec_c2r_partial(this->plan, out, in, d));
+    }
+    virtual void execC2C(void* out, const void* in, int direction, int d = 3) { DFFT_CALL(dfft_exec_c2c_partial(this->plan, out, in, direction, d)); }
+    // getPartitionDimensions(input_dim, transposed_dim, output_dim) — mpicufft_pencil.hpp:112-116
+    void getPartitionDimensions(Partition_Dimensions& in_, Partition_Dimensions& tr_, Partition_Dimensions& out_) {
+        const size_t nzc = this->transform == DFFT_C2C ? gs_.Nz : gs_.Nz / 2 + 1;
+        auto fill = [](std::vector<size_t>& size, std::vector<size_t>& start, size_t n, size_t parts) {
+            size.resize(parts); start.resize(parts);
+            dfft_partition(n, parts, size.data(), start.data());
+        };
+        fill(in_.size_x, in_.start_x, gs_.Nx, part_.P1); fill(in_.size_y, in_.start_y, gs_.Ny, part_.P2); fill(in_.size_z, in_.start_z, gs_.Nz, 1);
+        fill(tr_.size_x, tr_.start_x, gs_.Nx, part_.P1); fill(tr_.size_y, tr_.start_y, gs_.Ny, 1); fill(tr_.size_z, tr_.start_z, nzc, part_.P2);
+        fill(out_.size_x, out_.start_x, gs_.Nx, 1); fill(out_.size_y, out_.start_y, gs_.Ny, part_.P1); fill(out_.size_z, out_.start_z, nzc, part_.P2);
+    }
+
+private:
+    GlobalSize gs_{1, 1, 2};
+    Partition part_{1, 1};
+};
