@@ -1,5 +1,7 @@
 // fft_inst.cu — compiled once per (precision, log2 length): -DDFFT_T=double -DDFFT_LOG2N=10.
 // Splitting the instantiations over translation units lets build.py compile them in parallel.
+#include <cstdlib>
+
 #include "fft_kernels.cuh"
 
 #ifndef DFFT_T
@@ -12,6 +14,26 @@ template <typename K>
 static cudaError_t set_smem(K kernel, size_t bytes) {
     if (bytes <= 48 * 1024) return cudaSuccess;
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+}
+
+// persistent-kernel grid: resident CTAs per SM (queried once per kernel) x SM count
+template <typename K>
+static int persistent_ctas(K kernel, int threads, size_t smem) {
+    int dev = 0, sms = 0, per = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, threads, smem) != cudaSuccess || per < 1) per = 1;
+    return sms * per;
+}
+
+// DFFT_PIPE=0 forces the one-tile-per-CTA kernels, DFFT_PIPE=1 (default) uses the persistent
+// register-prefetch kernels where the tile shape allows 255 registers per thread.
+static int pipe_mode() {
+    static int mode = [] {
+        const char* e = getenv("DFFT_PIPE");
+        return e ? atoi(e) : 1;
+    }();
+    return mode;
 }
 
 template <typename T, int LOG2N>
@@ -31,6 +53,19 @@ cudaError_t launch_pass(PassKind kind, const FftParams& p, cudaStream_t stream) 
             if (p.in.sN != 1 || p.out.sN != 1) return cudaErrorInvalidValue;
             const long long grid = (lines + S::TBC - 1) / S::TBC;
             if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+            if constexpr (C::THREADS <= (sizeof(T) == 8 ? 256 : 512)) {
+                if (pipe_mode()) {
+                    auto pf = fft_c2c_pipe_kernel<T, LOG2N, LOG2E, S::TBC, false, false>;
+                    auto pi = fft_c2c_pipe_kernel<T, LOG2N, LOG2E, S::TBC, false, true>;
+                    static cudaError_t oncep = set_smem(pf, C::SMEM_BYTES) != cudaSuccess ? cudaErrorInvalidValue : set_smem(pi, C::SMEM_BYTES);
+                    if (oncep != cudaSuccess) return oncep;
+                    static int ctas = persistent_ctas(pf, C::THREADS, C::SMEM_BYTES);
+                    const unsigned g = unsigned(grid < ctas ? grid : ctas);
+                    if (p.inverse) pi<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
+                    else pf<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
+                    break;
+                }
+            }
             if (p.inverse) ki<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
             else kf<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
             break;
@@ -44,6 +79,19 @@ cudaError_t launch_pass(PassKind kind, const FftParams& p, cudaStream_t stream) 
             if (p.B <= 0) return cudaSuccess;
             const long long grid = lines * ((p.B + S::TBT - 1) / S::TBT);
             if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+            if constexpr (C::THREADS <= (sizeof(T) == 8 ? 256 : 512)) {
+                if (pipe_mode()) {
+                    auto pf = fft_c2c_pipe_kernel<T, LOG2N, LOG2E, S::TBT, true, false>;
+                    auto pi = fft_c2c_pipe_kernel<T, LOG2N, LOG2E, S::TBT, true, true>;
+                    static cudaError_t oncep = set_smem(pf, C::SMEM_BYTES) != cudaSuccess ? cudaErrorInvalidValue : set_smem(pi, C::SMEM_BYTES);
+                    if (oncep != cudaSuccess) return oncep;
+                    static int ctas = persistent_ctas(pf, C::THREADS, C::SMEM_BYTES);
+                    const unsigned g = unsigned(grid < ctas ? grid : ctas);
+                    if (p.inverse) pi<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
+                    else pf<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
+                    break;
+                }
+            }
             if (p.inverse) ki<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
             else kf<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
             break;
