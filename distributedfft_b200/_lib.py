@@ -79,6 +79,8 @@ SIGNATURES = {
     "dfft_get_phase_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),
     "dfft_get_last_breakdown": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "dfft_get_last_launch_count": (C.c_int, [C.c_void_p]),
+    "dfft_timer_gather": (C.c_int, [C.c_void_p]),
+    "dfft_timer_csv_path": (C.c_char_p, [C.c_void_p]),
     "dfft_last_error_string": (C.c_char_p, []),
     "dfft_version": (C.c_int, []),
     "dfft_fft1d_contig": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,

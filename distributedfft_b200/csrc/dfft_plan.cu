@@ -18,7 +18,11 @@
 #include <cuda_runtime.h>
 #include <nccl.h>
 
+#include <sys/stat.h>
+
+#include <chrono>
 #include <cmath>
+#include <fstream>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -223,6 +227,9 @@ struct dfft_plan_s {
     int n_events_used = 0;
     int last_launches = 0;
     int execs = 0;
+    double init_ms = 0;          // "init" section of the reference's CSV
+    int csv_warmup_left = 0;     // execs still to be skipped (Configurations::warmup_rounds)
+    std::string csv_path;        // empty: no CSV
 };
 
 namespace dfft {
@@ -828,6 +835,7 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
     return DFFT_SUCCESS;
 }
 
+static int timer_gather(dfft_plan_s* p);
 static int exec_common(dfft_plan_t p, void* out, const void* in, int inverse, int d, int need_transform, void* stream, bool sync) {
     // sync == true: the plain calls run on the plan's own stream; _async calls use exactly the stream given
     // (NULL = the CUDA default stream)
@@ -847,7 +855,81 @@ static int exec_common(dfft_plan_t p, void* out, const void* in, int inverse, in
     cudaStream_t st = sync ? p->own_stream : (cudaStream_t)stream;
     int rc = run_schedule(p, sc, out, in, st);
     if (rc) return rc;
-    if (sync) return dfft_plan_wait(p);
+    if (!sync) return DFFT_SUCCESS;
+    rc = dfft_plan_wait(p);
+    if (rc) return rc;
+    // the reference gathers and appends the section times after every non-warm-up exec
+    // (mpicufft_slab.cpp:817-821)
+    if (!p->csv_path.empty() && p->timing && d == 3) {
+        if (p->csv_warmup_left > 0) p->csv_warmup_left--;
+        else return timer_gather(p);
+    }
+    return DFFT_SUCCESS;
+}
+
+// =====================================================================================================
+// phase-timer CSV in the reference's on-disk schema (/root/reference/src/timer.cpp:58-101; file names
+// mpicufft_slab.cpp:99-103, mpicufft_slab_z_then_yx.cpp:76-80, mpicufft_pencil.cpp:67-72)
+// =====================================================================================================
+static const char* const SECTIONS_SLAB[] = {"init", "2D FFT (Sync)", "2D FFT Y-Z-Direction", "Transpose (First Send)", "Transpose (Packing)",
+    "Transpose (Start Local Transpose)", "Transpose (Start Receive)", "Transpose (First Receive)", "Transpose (Finished Receive)",
+    "Transpose (Start All2All)", "Transpose (Finished All2All)", "Transpose (Unpacking)", "1D FFT X-Direction", "Run complete"};
+static const char* const SECTIONS_ZYX[] = {"init", "1D FFT Z-Direction", "Transpose (First Send)", "Transpose (Packing)",
+    "Transpose (Start Local Transpose)", "Transpose (Start Receive)", "Transpose (First Receive)", "Transpose (Finished Receive)",
+    "Transpose (Start All2All)", "Transpose (Finished All2All)", "Transpose (Unpacking)", "2D FFT Y-X-Direction", "Run complete"};
+static const char* const SECTIONS_PENCIL[] = {"init", "1D FFT Z-Direction", "First Transpose (First Send)", "First Transpose (Packing)",
+    "First Transpose (Start Local Transpose)", "First Transpose (Start Receive)", "First Transpose (First Receive)",
+    "First Transpose (Finished Receive)", "First Transpose (Start All2All)", "First Transpose (Finished All2All)",
+    "First Transpose (Unpacking)", "First Transpose (Send Complete)", "1D FFT Y-Direction", "Second Transpose (First Send)",
+    "Second Transpose (Packing)", "Second Transpose (Start Local Transpose)", "Second Transpose (Start Receive)",
+    "Second Transpose (First Receive)", "Second Transpose (Finished Receive)", "Second Transpose (Start All2All)",
+    "Second Transpose (Finished All2All)", "Second Transpose (Unpacking)", "1D FFT X-Direction", "Run complete"};
+
+static void plan_sections(const dfft_plan_s* p, const char* const** list, int* n) {
+    if (p->g.decomp == DFFT_PENCIL) { *list = SECTIONS_PENCIL; *n = int(sizeof(SECTIONS_PENCIL) / sizeof(char*)); }
+    else if (p->g.decomp == DFFT_SLAB_Z_THEN_YX) { *list = SECTIONS_ZYX; *n = int(sizeof(SECTIONS_ZYX) / sizeof(char*)); }
+    else { *list = SECTIONS_SLAB; *n = int(sizeof(SECTIONS_SLAB) / sizeof(char*)); }
+}
+
+static int timer_gather(dfft_plan_s* p) {
+    if (p->n_events_used < 2) return fail(DFFT_ERR_STATE, "no timed exec to gather");
+    const char* const* names = nullptr;
+    int ns = 0;
+    plan_sections(p, &names, &ns);
+    std::vector<double> dur(ns, 0.0);
+    dur[0] = p->init_ms;
+    CK_CUDA(cudaEventSynchronize(p->events[p->n_events_used - 1]));
+    double last = 0;
+    for (int k = 1; k < p->n_events_used; ++k) {
+        float f = 0;
+        CK_CUDA(cudaEventElapsedTime(&f, p->events[0], p->events[k]));
+        last = f;
+        if (!p->ev_names[k]) continue;
+        for (int i = 0; i < ns; ++i)
+            if (!strcmp(names[i], p->ev_names[k])) dur[i] = f;
+    }
+    dur[ns - 1] = last;  // "Run complete"
+    std::vector<char> all;
+    int rc = nccl_allgather_bytes(p, dur.data(), sizeof(double) * ns, all);
+    if (rc) return rc;
+    if (p->rank != 0 || p->csv_path.empty()) return DFFT_SUCCESS;
+    const double* o = reinterpret_cast<const double*>(all.data());
+    struct stat sb;
+    std::ofstream f;
+    if (stat(p->csv_path.c_str(), &sb) != 0) {
+        f.open(p->csv_path);
+        f << ",";
+        for (int i = 0; i < p->P; ++i) f << i << ",";
+    } else {
+        f.open(p->csv_path, std::ios_base::app);
+    }
+    if (!f) return fail(DFFT_ERR_INVALID, "cannot open " + p->csv_path);
+    f << "\n";
+    for (int i = 0; i < ns; ++i) {
+        f << names[i] << ",";
+        for (int r = 0; r < p->P; ++r) f << o[size_t(r) * ns + i] << ",";
+        f << "\n";
+    }
     return DFFT_SUCCESS;
 }
 
@@ -918,6 +1000,7 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
     if (precision != DFFT_F32 && precision != DFFT_F64) return fail(DFFT_ERR_INVALID, "bad precision");
     if (transform != DFFT_R2C && transform != DFFT_C2C) return fail(DFFT_ERR_INVALID, "bad transform");
     CK_CUDA(cudaSetDevice(comm->device));
+    const auto t_init0 = std::chrono::steady_clock::now();
     dfft_plan_s* p = new dfft_plan_s();
     p->comm = comm;
     if (config) {
@@ -983,6 +1066,21 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         dfft_plan_destroy(p);
         g_err = keep;
         return rc;
+    }
+    p->init_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_init0).count();
+    if (!p->bench_dir.empty()) {
+        // <dir>/<variant>/test_0_<comm>_<snd>[_<comm2>_<snd2>]_<Nx>_<Ny>_<Nz>_<cuda_aware>_<P | P1_P2>.csv
+        const char* variant = decomp == DFFT_PENCIL ? "pencil" : (decomp == DFFT_SLAB_Z_THEN_YX ? "slab_z_then_yx" : "slab_default");
+        mkdir(p->bench_dir.c_str(), 0777);
+        mkdir((p->bench_dir + "/" + variant).c_str(), 0777);
+        std::string f = p->bench_dir + "/" + variant + "/test_0_" + std::to_string(p->cfg.comm_method) + "_" + std::to_string(p->cfg.send_method);
+        if (decomp == DFFT_PENCIL) f += "_" + std::to_string(p->cfg.comm_method2) + "_" + std::to_string(p->cfg.send_method2);
+        f += "_" + std::to_string(nx) + "_" + std::to_string(ny) + "_" + std::to_string(nz) + "_" + std::to_string(p->cfg.cuda_aware ? 1 : 0);
+        if (decomp == DFFT_PENCIL) f += "_" + std::to_string(g.P1) + "_" + std::to_string(g.P2);
+        else f += "_" + std::to_string(P);
+        p->csv_path = f + ".csv";
+        p->csv_warmup_left = p->cfg.warmup_rounds;
+        p->timing = true;
     }
     *plan = p;
     return DFFT_SUCCESS;
@@ -1127,6 +1225,11 @@ int dfft_get_last_breakdown(dfft_plan_t p, double* fft_ms, double* exchange_ms, 
     return DFFT_SUCCESS;
 }
 int dfft_get_last_launch_count(dfft_plan_t p) { return p ? p->last_launches : 0; }
+int dfft_timer_gather(dfft_plan_t p) {
+    if (!p) return fail(DFFT_ERR_INVALID, "null plan");
+    return timer_gather(p);
+}
+const char* dfft_timer_csv_path(dfft_plan_t p) { return p ? p->csv_path.c_str() : nullptr; }
 
 // ---- single-axis building blocks -----------------------------------------------------------------------
 static std::map<std::pair<int, int>, void*> g_tw_cache, g_tw2_cache;  // (prec, log2n)

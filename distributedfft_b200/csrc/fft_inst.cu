@@ -26,14 +26,52 @@ static int persistent_ctas(K kernel, int threads, size_t smem) {
     return sms * per;
 }
 
-// DFFT_PIPE=0 forces the one-tile-per-CTA kernels, DFFT_PIPE=1 (default) uses the persistent
-// register-prefetch kernels where the tile shape allows 255 registers per thread.
+// DFFT_PIPE=1 selects the persistent register-prefetch kernels where the tile shape allows 255 registers
+// per thread (measured slower than two resident CTAs per SM on B200 for most shapes, so off by default).
 static int pipe_mode() {
     static int mode = [] {
         const char* e = getenv("DFFT_PIPE");
-        return e ? atoi(e) : 1;
+        return e ? atoi(e) : 0;
     }();
     return mode;
+}
+
+static int wide_tiles() {
+    static int mode = [] {
+        const char* e = getenv("DFFT_WIDE_TILES");
+        return e ? atoi(e) : 0;
+    }();
+    return mode;
+}
+
+template <typename T, int LOG2N, int TB>
+static cudaError_t launch_tiled(const FftParams& p, cudaStream_t stream, long long lines) {
+    using S = Shape<T, LOG2N>;
+    constexpr int LOG2E = S::LOG2E;
+    using C = CtaFft<T, LOG2N, LOG2E, TB, true>;
+    auto kf = fft_c2c_kernel<T, LOG2N, LOG2E, TB, true, false>;
+    auto ki = fft_c2c_kernel<T, LOG2N, LOG2E, TB, true, true>;
+    static cudaError_t once = set_smem(kf, C::SMEM_BYTES) != cudaSuccess ? cudaErrorInvalidValue : set_smem(ki, C::SMEM_BYTES);
+    if (once != cudaSuccess) return once;
+    if (p.B <= 0) return cudaSuccess;
+    const long long grid = lines * ((p.B + TB - 1) / TB);
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    if constexpr (C::THREADS <= (sizeof(T) == 8 ? 256 : 512)) {
+        if (pipe_mode()) {
+            auto pf = fft_c2c_pipe_kernel<T, LOG2N, LOG2E, TB, true, false>;
+            auto pi = fft_c2c_pipe_kernel<T, LOG2N, LOG2E, TB, true, true>;
+            static cudaError_t oncep = set_smem(pf, C::SMEM_BYTES) != cudaSuccess ? cudaErrorInvalidValue : set_smem(pi, C::SMEM_BYTES);
+            if (oncep != cudaSuccess) return oncep;
+            static int ctas = persistent_ctas(pf, C::THREADS, C::SMEM_BYTES);
+            const unsigned g = unsigned(grid < ctas ? grid : ctas);
+            if (p.inverse) pi<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
+            else pf<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
+            return cudaGetLastError();
+        }
+    }
+    if (p.inverse) ki<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
+    else kf<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
+    return cudaGetLastError();
 }
 
 template <typename T, int LOG2N>
@@ -71,30 +109,11 @@ cudaError_t launch_pass(PassKind kind, const FftParams& p, cudaStream_t stream) 
             break;
         }
         case PASS_C2C_TILED: {
-            using C = CtaFft<T, LOG2N, LOG2E, S::TBT, true>;
-            auto kf = fft_c2c_kernel<T, LOG2N, LOG2E, S::TBT, true, false>;
-            auto ki = fft_c2c_kernel<T, LOG2N, LOG2E, S::TBT, true, true>;
-            static cudaError_t once = set_smem(kf, C::SMEM_BYTES) != cudaSuccess ? cudaErrorInvalidValue : set_smem(ki, C::SMEM_BYTES);
-            if (once != cudaSuccess) return once;
-            if (p.B <= 0) return cudaSuccess;
-            const long long grid = lines * ((p.B + S::TBT - 1) / S::TBT);
-            if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-            if constexpr (C::THREADS <= (sizeof(T) == 8 ? 256 : 512)) {
-                if (pipe_mode()) {
-                    auto pf = fft_c2c_pipe_kernel<T, LOG2N, LOG2E, S::TBT, true, false>;
-                    auto pi = fft_c2c_pipe_kernel<T, LOG2N, LOG2E, S::TBT, true, true>;
-                    static cudaError_t oncep = set_smem(pf, C::SMEM_BYTES) != cudaSuccess ? cudaErrorInvalidValue : set_smem(pi, C::SMEM_BYTES);
-                    if (oncep != cudaSuccess) return oncep;
-                    static int ctas = persistent_ctas(pf, C::THREADS, C::SMEM_BYTES);
-                    const unsigned g = unsigned(grid < ctas ? grid : ctas);
-                    if (p.inverse) pi<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
-                    else pf<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
-                    break;
-                }
+            // DFFT_WIDE_TILES=1: twice the tile width (128-byte rows for the long lengths) at one CTA per SM
+            if constexpr (S::TBT_WIDE != S::TBT) {
+                if (wide_tiles()) return launch_tiled<T, LOG2N, S::TBT_WIDE>(p, stream, lines);
             }
-            if (p.inverse) ki<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
-            else kf<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
-            break;
+            return launch_tiled<T, LOG2N, S::TBT>(p, stream, lines);
         }
         case PASS_R2C: {
             using C = CtaFft<T, LOG2N, LOG2E, S::TBC, false>;

@@ -74,6 +74,8 @@ struct Shape {
     static constexpr int CAP2 = 1024 / TPL;
     static constexpr int CAP = CAP1 < CAP2 ? CAP1 : CAP2;
     static constexpr int TBT = TBT_ > CAP ? (CAP < 1 ? 1 : CAP) : TBT_;
+    // experimental wider tile (DFFT_WIDE_TILES=1): double width if it still fits 128 KB / 1024 threads
+    static constexpr int TBT_WIDE = (2 * TBT <= CAP && 2 * TBT <= 32) ? 2 * TBT : TBT;
 };
 
 template <typename T>

@@ -157,6 +157,11 @@ int dfft_timer_enable(dfft_plan_t plan, int enable);
 int dfft_get_phase_count(dfft_plan_t plan);
 const char* dfft_get_phase_name(dfft_plan_t plan, int i);
 int dfft_get_phase_times(dfft_plan_t plan, double* ms, int capacity);
+/* Collective: gathers the section times of the last timed exec to rank 0, which appends one block to the CSV
+ * in the reference's schema (src/timer.cpp:58-101).  Called automatically after every non-warm-up
+ * synchronous exec when Configurations::benchmark_dir is set. */
+int dfft_timer_gather(dfft_plan_t plan);
+const char* dfft_timer_csv_path(dfft_plan_t plan);
 /* GPU time of the local FFT passes and of the exchange steps of the last timed exec (ms). */
 int dfft_get_last_breakdown(dfft_plan_t plan, double* fft_ms, double* exchange_ms, double* total_ms);
 
