@@ -80,6 +80,9 @@ SIGNATURES = {
     "dfft_get_last_breakdown": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "dfft_get_last_launch_count": (C.c_int, [C.c_void_p]),
     "dfft_timer_gather": (C.c_int, [C.c_void_p]),
+    "dfft_get_step_count": (C.c_int, [C.c_void_p]),
+    "dfft_get_step_label": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "dfft_get_step_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),
     "dfft_timer_csv_path": (C.c_char_p, [C.c_void_p]),
     "dfft_last_error_string": (C.c_char_p, []),
     "dfft_version": (C.c_int, []),

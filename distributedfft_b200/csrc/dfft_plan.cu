@@ -170,6 +170,7 @@ enum StepType { STEP_PASS = 0, STEP_RENDEZVOUS = 1, STEP_A2A = 2 };
 struct Step {
     StepType type = STEP_PASS;
     const char* phase = nullptr;  // timer section recorded after this step
+    const char* label = "";       // short name of the step ("z pass", "y pass", "rendezvous 2", ...)
     // PASS
     PassKind kind = PASS_C2C_CONTIG;
     int log2n = 0;
@@ -224,6 +225,7 @@ struct dfft_plan_s {
     std::vector<cudaEvent_t> events;
     std::vector<const char*> ev_names;
     std::vector<int> ev_is_fft;  // 1 fft pass, 0 exchange
+    std::vector<const char*> ev_labels;
     int n_events_used = 0;
     int last_launches = 0;
     int execs = 0;
@@ -305,6 +307,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
     auto new_pass = [&](PassKind kind, size_t n, const char* phase, Step& s) -> int {
         s = Step();
         s.type = STEP_PASS;
+        s.label = (kind == PASS_C2C_TILED) ? "strided pass" : (kind == PASS_R2C ? "z pass (R2C)" : (kind == PASS_C2R ? "z pass (C2R)" : "z pass"));
         s.kind = kind;
         s.phase = phase;
         s.log2n = ilog2_exact(n);
@@ -326,6 +329,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
     auto rendezvous = [&](int group, int phase_id, const char* phase) {
         Step s;
         s.type = STEP_RENDEZVOUS;
+        s.label = group == 0 ? "entry rendezvous" : (group == 1 ? "rendezvous 1" : "rendezvous 2");
         s.group = group;
         s.phase_id = phase_id;
         s.phase = phase;
@@ -370,6 +374,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
 
     auto a2a_counts = [&](Step& s, const std::vector<int>& G, auto send_elems, auto recv_elems) {
         s.type = STEP_A2A;
+        s.label = "nccl all-to-all";
         size_t so = 0, ro = 0;
         s.scount.resize(G.size()); s.soff.resize(G.size()); s.rcount.resize(G.size()); s.roff.resize(G.size());
         for (size_t q = 0; q < G.size(); ++q) {
@@ -442,6 +447,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
         const size_t nx2 = zyx ? g.nx : nx_i;  // x extent held after transposition 1
         rc = new_pass(PASS_C2C_TILED, g.ny, g.decomp == DFFT_SLAB_ZY_THEN_X ? "2D FFT Y-Z-Direction" : (zyx ? nullptr : "1D FFT Y-Direction"), s2);
         if (rc) return rc;
+        s2.label = "y pass";
         s2.prm.A0 = int(nx2); s2.prm.A1 = 1; s2.prm.B = int(nz_j);
         if (t1_a2a && !zyx) {
             seg_view(s2.prm.in, tab_y_in, G1, [&](int q, int) {
@@ -467,6 +473,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
             Step s3;
             rc = new_pass(PASS_C2C_TILED, g.nx, "2D FFT Y-X-Direction", s3);
             if (rc) return rc;
+            s3.label = "x pass";
             s3.prm.A0 = 1; s3.prm.A1 = 1; s3.prm.B = int(g.ny * nz_j);
             s3.prm.in = single_view(s2.prm.in.seg[0].base, 0, 0, (long long)(g.ny * nz_j));
             s3.prm.out = single_view(nullptr, 0, 0, (long long)(g.ny * nz_j));
@@ -499,6 +506,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
         Step s3;
         rc = new_pass(PASS_C2C_TILED, g.nx, "1D FFT X-Direction", s3);
         if (rc) return rc;
+        s3.label = "x pass";
         s3.prm.A0 = 1; s3.prm.A1 = 1; s3.prm.B = int(oy_i * nz_j);
         s3.prm.in = single_view(t2_a2a ? slotp(SR, me) : slotp(D2, me), 0, 0, (long long)(oy_i * nz_j));
         s3.prm.out = single_view(nullptr, 0, 0, (long long)(oy_i * nz_j));
@@ -534,6 +542,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
         Step sy_;
         rc = new_pass(PASS_C2C_TILED, g.ny, nullptr, sy_);
         if (rc) return rc;
+        sy_.label = "y pass";
         const int W = dir1 ? D2 : SR;  // a local scratch slot that is not the transposition target
         sy_.prm.A0 = int(g.nx); sy_.prm.B = int(nz_j);
         sy_.prm.in = single_view(nullptr, (long long)(g.ny * nz_j), 0, (long long)nz_j);
@@ -543,6 +552,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
         Step sx_;
         rc = new_pass(PASS_C2C_TILED, g.nx, "2D FFT Y-X-Direction", sx_);
         if (rc) return rc;
+        sx_.label = "x pass";
         sx_.prm.A0 = 1; sx_.prm.A1 = int(g.ny); sx_.prm.B = int(nz_j);
         sx_.prm.in = single_view(slotp(W, me), 0, (long long)nz_j, (long long)(g.ny * nz_j));
         Step xa;
@@ -584,6 +594,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
         Step s3;
         rc = new_pass(PASS_C2C_TILED, g.nx, "1D FFT X-Direction", s3);
         if (rc) return rc;
+        s3.label = "x pass";
         s3.prm.A0 = 1; s3.prm.A1 = 1; s3.prm.B = int(oy_i * nz_j);
         s3.prm.in = single_view(nullptr, 0, 0, (long long)(oy_i * nz_j));
         s3.in_user = 1;
@@ -607,6 +618,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
     Step s2;
     rc = new_pass(PASS_C2C_TILED, g.ny, slab ? nullptr : "1D FFT Y-Direction", s2);
     if (rc) return rc;
+    s2.label = "y pass";
     s2.prm.A0 = int(nx_i); s2.prm.A1 = 1; s2.prm.B = int(nz_j);
     if (!have_in_slot) {
         s2.prm.in = single_view(nullptr, (long long)(g.ny * nz_j), 0, (long long)nz_j);
@@ -778,7 +790,7 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
     int launches = 0;
     int ev = 0;
     const bool timing = p->timing;
-    auto mark = [&](const char* name, int is_fft) -> cudaError_t {
+    auto mark = [&](const char* name, int is_fft, const char* label = "") -> cudaError_t {
         if (!timing) return cudaSuccess;
         if (ev >= int(p->events.size())) {
             cudaEvent_t e;
@@ -787,9 +799,11 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
             p->events.push_back(e);
             p->ev_names.push_back(name);
             p->ev_is_fft.push_back(is_fft);
+            p->ev_labels.push_back(label);
         }
         p->ev_names[ev] = name;
         p->ev_is_fft[ev] = is_fft;
+        p->ev_labels[ev] = label;
         return cudaEventRecord(p->events[ev++], st);
     };
     CK_CUDA(mark("start", -1));
@@ -801,7 +815,7 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
             cudaError_t e = p->prec == DFFT_F64 ? launch_pass_f64(s.log2n, s.kind, prm, st) : launch_pass_f32(s.log2n, s.kind, prm, st);
             if (e != cudaSuccess) return fail(DFFT_ERR_CUDA, std::string("FFT pass launch failed: ") + cudaGetErrorString(e));
             ++launches;
-            CK_CUDA(mark(s.phase, 1));
+            CK_CUDA(mark(s.phase, 1, s.label));
         } else if (s.type == STEP_RENDEZVOUS) {
             const std::vector<int>& G = p->grp[s.group];
             if (G.size() > 1) {
@@ -810,7 +824,7 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
                 CK_CUDA(cudaGetLastError());
                 ++launches;
             }
-            CK_CUDA(mark(s.phase, 0));
+            CK_CUDA(mark(s.phase, 0, s.label));
         } else {
             const std::vector<int>& G = p->grp[s.group];
             char* sb = (char*)p->slot_ptr[s.send_slot][me];
@@ -825,7 +839,7 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
             for (size_t q = 0; q < G.size(); ++q)
                 if (G[q] == me && s.scount[q])
                     CK_CUDA(cudaMemcpyAsync(rb + s.roff[q] * es, sb + s.soff[q] * es, s.scount[q] * es, cudaMemcpyDeviceToDevice, st));
-            CK_CUDA(mark(s.phase, 0));
+            CK_CUDA(mark(s.phase, 0, s.label));
         }
     }
     CK_CUDA(mark("Run complete", -1));
@@ -1225,6 +1239,24 @@ int dfft_get_last_breakdown(dfft_plan_t p, double* fft_ms, double* exchange_ms, 
     return DFFT_SUCCESS;
 }
 int dfft_get_last_launch_count(dfft_plan_t p) { return p ? p->last_launches : 0; }
+int dfft_get_step_count(dfft_plan_t p) { return p && p->n_events_used > 1 ? p->n_events_used - 2 : 0; }
+const char* dfft_get_step_label(dfft_plan_t p, int i) {
+    if (!p || i < 0 || i + 1 >= p->n_events_used - 1) return nullptr;
+    return p->ev_labels[i + 1];
+}
+int dfft_get_step_times(dfft_plan_t p, double* ms, int capacity) {
+    if (!p || !ms) return fail(DFFT_ERR_INVALID, "null argument");
+    if (p->n_events_used < 2) return fail(DFFT_ERR_STATE, "no timed exec yet (dfft_timer_enable)");
+    CK_CUDA(cudaEventSynchronize(p->events[p->n_events_used - 1]));
+    int n = 0;
+    for (int k = 1; k < p->n_events_used - 1; ++k, ++n) {
+        if (n >= capacity) continue;
+        float f = 0;
+        CK_CUDA(cudaEventElapsedTime(&f, p->events[k - 1], p->events[k]));
+        ms[n] = f;
+    }
+    return n;
+}
 int dfft_timer_gather(dfft_plan_t p) {
     if (!p) return fail(DFFT_ERR_INVALID, "null plan");
     return timer_gather(p);

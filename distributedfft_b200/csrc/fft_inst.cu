@@ -109,9 +109,14 @@ cudaError_t launch_pass(PassKind kind, const FftParams& p, cudaStream_t stream) 
             break;
         }
         case PASS_C2C_TILED: {
-            // DFFT_WIDE_TILES=1: twice the tile width (128-byte rows for the long lengths) at one CTA per SM
+            // Wide tiles (128-byte rows, one CTA per SM) win when the rows of a tile sit in different 2 MB pages
+            // (x passes with a row pitch >= 1 MiB: 3012 -> 3863 GB/s at N=1024 f64) and lose otherwise
+            // (y passes: 4611 -> 3876 GB/s).  DFFT_WIDE_TILES=1 / -1 forces them on / off.
             if constexpr (S::TBT_WIDE != S::TBT) {
-                if (wide_tiles()) return launch_tiled<T, LOG2N, S::TBT_WIDE>(p, stream, lines);
+                const int w = wide_tiles();
+                const bool far_rows = (unsigned long long)p.in.sN * sizeof(cx<T>) >= (1ull << 20) ||
+                                      (unsigned long long)p.out.sN * sizeof(cx<T>) >= (1ull << 20);
+                if (w > 0 || (w == 0 && LOG2N >= 10 && far_rows)) return launch_tiled<T, LOG2N, S::TBT_WIDE>(p, stream, lines);
             }
             return launch_tiled<T, LOG2N, S::TBT>(p, stream, lines);
         }

@@ -191,6 +191,13 @@ class MPIcuFFT:
         n = check(lib().dfft_get_phase_times(self._h, ms, n))
         return [(lib().dfft_get_phase_name(self._h, i).decode(), float(ms[i])) for i in range(n)]
 
+    def stepTimes(self):
+        """[(label, ms)] per launched step of the last timed exec."""
+        n = lib().dfft_get_step_count(self._h)
+        ms = (C.c_double * max(n, 1))()
+        n = check(lib().dfft_get_step_times(self._h, ms, n))
+        return [(lib().dfft_get_step_label(self._h, i).decode(), float(ms[i])) for i in range(n)]
+
     def lastBreakdown(self):
         f, x, t = C.c_double(), C.c_double(), C.c_double()
         check(lib().dfft_get_last_breakdown(self._h, C.byref(f), C.byref(x), C.byref(t)))

@@ -157,6 +157,11 @@ int dfft_timer_enable(dfft_plan_t plan, int enable);
 int dfft_get_phase_count(dfft_plan_t plan);
 const char* dfft_get_phase_name(dfft_plan_t plan, int i);
 int dfft_get_phase_times(dfft_plan_t plan, double* ms, int capacity);
+/* Per-step GPU time of the last timed exec, in launch order: one entry per FFT pass / rendezvous / all-to-all
+ * (labels such as "z pass", "y pass", "x pass", "rendezvous 2", "nccl all-to-all"). */
+int dfft_get_step_count(dfft_plan_t plan);
+const char* dfft_get_step_label(dfft_plan_t plan, int i);
+int dfft_get_step_times(dfft_plan_t plan, double* ms, int capacity);
 /* Collective: gathers the section times of the last timed exec to rank 0, which appends one block to the CSV
  * in the reference's schema (src/timer.cpp:58-101).  Called automatically after every non-warm-up
  * synchronous exec when Configurations::benchmark_dir is set. */

@@ -152,3 +152,31 @@ def test_full_size_roundtrip_512():
     err = float((back / n - x).abs().max())
     assert err < 1e-12
     plan.destroy()
+
+
+def test_timer_csv_schema(tmp_path):
+    """Phase-timer CSV in the reference's on-disk schema (src/timer.cpp:58-101): header ',0,1,..,P-1,',
+    one row per section, blank line between execs; warm-up execs are skipped; file name as in
+    mpicufft_slab.cpp:99-103."""
+    cfg = dfft.Configurations(warmup_rounds=1, benchmark_dir=str(tmp_path))
+    plan = dfft.MPIcuFFT_Slab(cfg, dfft.Comm(), precision="double", transform="r2c")
+    plan.initFFT(dfft.GlobalSize(32, 32, 32), None, True)
+    x = dev(O.real_input((32, 32, 32)))
+    out = torch.empty((32, 32, 17), dtype=torch.complex128, device="cuda")
+    for _ in range(3):
+        plan.execR2C(out, x)
+    path = tmp_path / "slab_default" / "test_0_0_0_32_32_32_1_1.csv"
+    assert path.exists()
+    lines = path.read_text().split("\n")
+    assert lines[0] == ",0,"
+    blocks = [b for b in "\n".join(lines[1:]).split("\n\n") if b.strip()]
+    assert len(blocks) == 2  # 3 execs - 1 warm-up
+    rows = [r.split(",") for r in blocks[0].strip().split("\n")]
+    names = [r[0] for r in rows]
+    assert names[0] == "init" and names[-1] == "Run complete" and "2D FFT Y-Z-Direction" in names and "1D FFT X-Direction" in names
+    assert len(names) == 14
+    vals = {r[0]: float(r[1]) for r in rows}
+    assert 0 < vals["2D FFT Y-Z-Direction"] <= vals["1D FFT X-Direction"] <= vals["Run complete"]
+    steps = plan.stepTimes()
+    assert [l for l, _ in steps] == ["z pass (R2C)", "y pass", "x pass"]
+    plan.destroy()
