@@ -165,6 +165,7 @@ def main():
     ap.add_argument("--p1", type=int, default=0)
     ap.add_argument("--p2", type=int, default=0)
     ap.add_argument("--comm", default="Peer2Peer", choices=["Peer2Peer", "All2All"])
+    ap.add_argument("--send", default="auto", choices=["auto", "Sync", "Streams"], help="Streams = overlapped schedule (default for N > 1)")
     ap.add_argument("--prec", default="f64", choices=["f64", "f32"])
     ap.add_argument("--transform", default="c2c", choices=["c2c", "r2c"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
@@ -198,19 +199,24 @@ def main():
     rdt = torch.float64 if f64 else torch.float32
     es = 16 if f64 else 8
     cm = dfft.CommunicationMethod.Peer2Peer if args.comm == "Peer2Peer" else dfft.CommunicationMethod.All2All
-    cfg = dfft.Configurations(comm_method=cm, comm_method2=cm)
+    send = args.send if args.send != "auto" else ("Streams" if world > 1 else "Sync")
+    sm = dfft.SendMethod.Streams if send == "Streams" else dfft.SendMethod.Sync
+    cfg = dfft.Configurations(comm_method=cm, comm_method2=cm, send_method=sm)
     c2c = args.transform == "c2c"
-    if args.decomp == "pencil":
-        p1 = args.p1 or (2 if world >= 2 else 1)
-        p2 = args.p2 or world // p1
-        plan = dfft.MPIcuFFT_Pencil(cfg, comm, precision="double" if f64 else "float", transform=args.transform)
-        plan.initFFT(dfft.GlobalSize(*shape), dfft.Pencil_Partition(p1, p2), True)
-        par = f"pencil{p1}x{p2}"
-    else:
+
+    def make_plan(config):
+        if args.decomp == "pencil":
+            p1 = args.p1 or (2 if world >= 2 else 1)
+            p2 = args.p2 or world // p1
+            pl = dfft.MPIcuFFT_Pencil(config, comm, precision="double" if f64 else "float", transform=args.transform)
+            pl.initFFT(dfft.GlobalSize(*shape), dfft.Pencil_Partition(p1, p2), True)
+            return pl, f"pencil{p1}x{p2}"
         cls = dfft.MPIcuFFT_Slab if args.decomp == "slab" else dfft.MPIcuFFT_Slab_Z_Then_YX
-        plan = cls(cfg, comm, precision="double" if f64 else "float", transform=args.transform)
-        plan.initFFT(dfft.GlobalSize(*shape), None, True)
-        par = f"{args.decomp}{world}"
+        pl = cls(config, comm, precision="double" if f64 else "float", transform=args.transform)
+        pl.initFFT(dfft.GlobalSize(*shape), None, True)
+        return pl, f"{args.decomp}{world}"
+
+    plan, par = make_plan(cfg)
     isz, osz = plan.getInSize(), plan.getOutSize()
     n_in = isz[0] * isz[1] * isz[2]
     dom = plan.getDomainSize() // es
@@ -258,21 +264,36 @@ def main():
     fl = flops_c2c(shape) * (1.0 if c2c else 0.5)
     value = fl / (ms_step * 1e-3) / 1e9
 
-    # per-step breakdown (separate loop: CUDA events between the steps of one exec)
-    plan.enableTimer(True)
+    # per-step breakdown (separate loop: CUDA events between the steps of one exec).  The overlapped
+    # (Streams) schedule has no meaningful per-step times, so the breakdown runs the sequential schedule.
+    if send == "Streams":
+        bplan, _ = make_plan(dfft.Configurations(comm_method=cm, comm_method2=cm, send_method=dfft.SendMethod.Sync))
+    else:
+        bplan = plan
+
+    def bstep():
+        if c2c:
+            bplan.execC2C(out, x, dfft.FORWARD, stream=stream)
+        else:
+            bplan.execR2C(out, x, stream=stream)
+
+    bplan.enableTimer(True)
     reps = max(3, min(10, args.steps))
     acc_steps, acc_cum, bd_acc = None, None, None
     for _ in range(reps):
         barrier()
-        step()
-        plan.wait()
-        st = plan.stepTimes()
-        pt = plan.phaseTimes()
-        bd = plan.lastBreakdown()
+        bstep()
+        bplan.wait()
+        st = bplan.stepTimes()
+        pt = bplan.phaseTimes()
+        bd = bplan.lastBreakdown()
         acc_steps = [t for _, t in st] if acc_steps is None else [a + t for a, (_, t) in zip(acc_steps, st)]
         acc_cum = [t for _, t in pt] if acc_cum is None else [a + t for a, (_, t) in zip(acc_cum, pt)]
         bd_acc = dict(bd) if bd_acc is None else {k: bd_acc[k] + bd[k] for k in bd}
-    plan.enableTimer(False)
+    bplan.enableTimer(False)
+    seq_ms = bd_acc["total_ms"] / reps
+    if bplan is not plan:
+        bplan.destroy()
     labels = [n for n, _ in st]
     step_ms = [a / reps for a in acc_steps]
     names = [n for n, _ in pt]
@@ -358,7 +379,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.prec, "data": "synthetic",
             "config": {"workload": f"{shape[0]}x{shape[1]}x{shape[2]} complex-{'double' if f64 else 'float'} "
                                    f"{'C2C' if c2c else 'R2C'} forward 3D FFT, {args.decomp} decomposition",
-                       "parallelism": par, "comm_method": args.comm, "points_per_gpu": int(ntot_local),
+                       "parallelism": par, "comm_method": args.comm, "send_method": send, "sequential_schedule_ms": seq_ms, "points_per_gpu": int(ntot_local),
                        "l2_policy": "inputs (>= 2 GiB per GPU) exceed the 126 MB L2; no flush needed",
                        "gflops_literal_5N3log2N_edge": (5.0 * shape[0] * shape[1] * shape[2] * math.log2(shape[0]) / (ms_step * 1e-3) / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

@@ -24,6 +24,7 @@
 #include <cmath>
 #include <fstream>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -181,11 +182,18 @@ struct Step {
     // A2A
     std::vector<size_t> scount, soff, rcount, roff;  // elements, indexed by group member
     int send_slot = 0, recv_slot = 0;
+    // overlapped schedules: which plan stream runs the step (0 = caller's stream, 1 = exchange stream,
+    // 2 = follow-up stream), events to wait for before it and the event to record after it
+    int stream = 0;
+    std::vector<int> waits;
+    int record = -1;
 };
 
 struct Schedule {
     std::vector<Step> steps;
     bool built = false;
+    bool overlapped = false;  // uses the plan's auxiliary streams
+    int nevents = 0;
 };
 
 }  // namespace dfft
@@ -216,6 +224,11 @@ struct dfft_plan_s {
     std::vector<int> grp[3];
     int* err_d = nullptr;
     unsigned long long epoch = 0;
+    unsigned long long ticket[4] = {0, 0, 0, 0};  // per-phase rendezvous counters (same sequence on every rank)
+    cudaStream_t aux[2] = {nullptr, nullptr};     // exchange stream (high priority), follow-up stream
+    std::vector<cudaEvent_t> sync_events;
+    cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
+    int xchg_ctas = 0;                            // SMs given to the exchange pass in overlapped schedules
     cudaStream_t own_stream = nullptr, last_stream = nullptr;  // last_stream: stream of the last exec
     Tables tabs;
     // schedules: [fwd/inv][d-1]
@@ -259,6 +272,7 @@ static View single_view(void* base, long long sA0, long long sA1, long long sN) 
 namespace dfft {
 
 static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc);
+static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc);
 
 }  // namespace dfft
 
@@ -669,6 +683,187 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
 
 }  // namespace dfft
 
+namespace dfft {
+
+// Overlapped slab (ZY_Then_X) schedule, Peer2Peer, SendMethod Streams.
+//
+// The reference's Streams variant overlaps pack(q+1) with send(q) (mpicufft_slab.cpp:398-415).  Here the
+// exchange is the y pass itself (NVLink-bound), so the overlap is between whole FFT passes:
+//   stream 0 (caller) : z pass, plane group by plane group                       (HBM-bound)
+//   stream 1 (exchange, high priority): y pass per (plane group, z chunk), persistent on `xchg_ctas`
+//                       SMs, storing straight into the peers' slots              (NVLink-bound)
+//   stream 2 (follow-up): per z chunk: rendezvous with the peers, then the x pass of that chunk (HBM-bound)
+// The y pass of chunk c+1 runs while the x pass consumes chunk c, and while later plane groups are still in
+// the z pass.  Inverse: x pass per z chunk scatters (stream 1), y pass per chunk follows (stream 2), the z
+// pass runs last on the caller's stream.
+static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
+    const Geometry& g = p->g;
+    const int me = p->rank;
+    const size_t es = p->esize;
+    const bool c2c = g.transform == DFFT_C2C;
+    Tables& T = p->tabs;
+    sc.steps.clear();
+    sc.overlapped = true;
+    const size_t nzc = g.nzc, ny = g.ny, nx = g.nx;
+    const size_t nx_p = g.sx.size[me], x0 = g.sx.start[me];
+    const size_t oy_me = g.oy.size[me], oy0_me = g.oy.start[me];
+    const std::vector<int>& G2 = p->grp[2];
+    const int D1 = 0, D2 = 1;
+    auto slotp = [&](int s_, int r) -> void* { return p->slot_ptr[s_][r]; };
+    int nev = 0;
+
+    auto new_pass = [&](PassKind kind, size_t n, const char* label, Step& s) -> int {
+        s = Step();
+        s.type = STEP_PASS;
+        s.kind = kind;
+        s.label = label;
+        s.log2n = ilog2_exact(n);
+        if (s.log2n < 1 || s.log2n > MAX_LOG2N) return fail(DFFT_ERR_UNSUPPORTED, "unsupported axis length");
+        s.prm.A0 = 1; s.prm.A1 = 1; s.prm.B = 1;
+        s.prm.inverse = inverse;
+        void* tw = nullptr;
+        if (T.get_tw(s.log2n, &tw) != cudaSuccess) return fail(DFFT_ERR_CUDA, "twiddle table allocation failed");
+        s.prm.tw = tw;
+        if (kind == PASS_R2C || kind == PASS_C2R) {
+            void* tw2 = nullptr;
+            if (T.get_tw2(s.log2n, &tw2) != cudaSuccess) return fail(DFFT_ERR_CUDA, "twiddle table allocation failed");
+            s.prm.tw2 = tw2;
+        }
+        return DFFT_SUCCESS;
+    };
+    auto rendezvous = [&](int group, int phase_id, int stream) {
+        Step s;
+        s.type = STEP_RENDEZVOUS;
+        s.label = group == 0 ? "entry rendezvous" : "rendezvous 2";
+        s.group = group;
+        s.phase_id = phase_id;
+        s.stream = stream;
+        return s;
+    };
+
+    // plane groups (of my x planes) and z chunks
+    Split groups, chunks;
+    const size_t NG = std::min<size_t>(4, nx_p);
+    const size_t NS = nzc >= 128 ? 4 : (nzc >= 32 ? 2 : 1);
+    groups.make(nx_p, NG);
+    chunks.make(nzc, NS);
+    const unsigned char *tab_y = nullptr, *tab_x = nullptr;
+    if (T.seg_table(g.oy, &tab_y) != cudaSuccess || T.seg_table(g.sx, &tab_x) != cudaSuccess) return fail(DFFT_ERR_CUDA, "segment table");
+
+    sc.steps.push_back(rendezvous(0, 0, 0));  // everyone has left the previous exec
+    // the auxiliary streams fork from the caller's stream at the start of run_schedule, i.e. BEFORE the
+    // entry rendezvous: make them wait for it explicitly
+    const int ev_entry = nev++;
+    sc.steps.back().record = ev_entry;
+    int rc;
+
+    if (!inverse) {
+        std::vector<int> ev_z(NG), ev_y(NS);
+        for (size_t gi = 0; gi < NG; ++gi) {
+            Step s;
+            rc = new_pass(c2c ? PASS_C2C_CONTIG : PASS_R2C, c2c ? g.nz : g.nz / 2, c2c ? "z pass" : "z pass (R2C)", s);
+            if (rc) return rc;
+            const size_t pl0 = groups.start[gi], npl = groups.size[gi];
+            const long long pitch = c2c ? (long long)g.nz : (long long)(g.nz / 2);
+            s.prm.A0 = int(npl); s.prm.A1 = int(ny);
+            s.prm.in = single_view((void*)(size_t)(pl0 * ny * pitch * es), pitch * (long long)ny, pitch, 1);
+            s.in_user = 1;
+            s.prm.out = single_view(eptr(slotp(D1, me), pl0 * ny * nzc, es), (long long)(ny * nzc), (long long)nzc, 1);
+            s.stream = 0;
+            s.record = ev_z[gi] = nev++;
+            sc.steps.push_back(s);
+        }
+        for (size_t c = 0; c < NS; ++c) {
+            const size_t z0 = chunks.start[c], zc = chunks.size[c];
+            for (size_t gi = 0; gi < NG; ++gi) {
+                Step s;
+                rc = new_pass(PASS_C2C_TILED, ny, "y pass", s);
+                if (rc) return rc;
+                const size_t pl0 = groups.start[gi], npl = groups.size[gi];
+                s.prm.A0 = int(npl); s.prm.A1 = 1; s.prm.B = int(zc);
+                s.prm.in = single_view(eptr(slotp(D1, me), pl0 * ny * nzc + z0, es), (long long)(ny * nzc), 0, (long long)nzc);
+                seg_view(s.prm.out, tab_y, G2, [&](int q, int r) {
+                    const size_t nyq = g.oy.size[q];
+                    return mkseg(eptr(slotp(D2, r), (x0 + pl0) * nyq * nzc + z0, es), (long long)(nyq * nzc), 0, (long long)nzc, g.oy.start[q]);
+                });
+                s.prm.max_ctas = p->xchg_ctas;
+                s.stream = 1;
+                if (c == 0) s.waits.push_back(ev_z[gi]);
+                if (c == 0 && gi == 0) s.waits.push_back(ev_entry);
+                if (gi + 1 == NG) s.record = ev_y[c] = nev++;
+                sc.steps.push_back(s);
+            }
+        }
+        for (size_t c = 0; c < NS; ++c) {
+            const size_t z0 = chunks.start[c], zc = chunks.size[c];
+            Step r = rendezvous(2, 2, 2);
+            r.waits.push_back(ev_y[c]);
+            sc.steps.push_back(r);
+            Step s;
+            rc = new_pass(PASS_C2C_TILED, nx, "x pass", s);
+            if (rc) return rc;
+            s.prm.A0 = 1; s.prm.A1 = int(oy_me); s.prm.B = int(zc);
+            s.prm.in = single_view(eptr(slotp(D2, me), z0, es), 0, (long long)nzc, (long long)(oy_me * nzc));
+            s.prm.out = single_view((void*)(size_t)(z0 * es), 0, (long long)nzc, (long long)(oy_me * nzc));
+            s.out_user = 2;
+            s.stream = 2;
+            sc.steps.push_back(s);
+        }
+    } else {
+        std::vector<int> ev_x(NS), ev_yi(NS);
+        for (size_t c = 0; c < NS; ++c) {
+            const size_t z0 = chunks.start[c], zc = chunks.size[c];
+            Step s;
+            rc = new_pass(PASS_C2C_TILED, nx, "x pass", s);
+            if (rc) return rc;
+            s.prm.A0 = 1; s.prm.A1 = int(oy_me); s.prm.B = int(zc);
+            s.prm.in = single_view((void*)(size_t)(z0 * es), 0, (long long)nzc, (long long)(oy_me * nzc));
+            s.in_user = 1;
+            // dest q holds [nx_q][ny][nzc]; my rows y in [oy0_me, +oy_me)
+            seg_view(s.prm.out, tab_x, G2, [&](int q, int r) {
+                return mkseg(eptr(slotp(D2, r), oy0_me * nzc + z0, es), 0, (long long)nzc, (long long)(ny * nzc), g.sx.start[q]);
+            });
+            s.prm.max_ctas = p->xchg_ctas;
+            s.stream = 1;
+            if (c == 0) s.waits.push_back(ev_entry);
+            s.record = ev_x[c] = nev++;
+            sc.steps.push_back(s);
+        }
+        for (size_t c = 0; c < NS; ++c) {
+            const size_t z0 = chunks.start[c], zc = chunks.size[c];
+            Step r = rendezvous(2, 2, 2);
+            r.waits.push_back(ev_x[c]);
+            sc.steps.push_back(r);
+            Step s;
+            rc = new_pass(PASS_C2C_TILED, ny, "y pass", s);
+            if (rc) return rc;
+            s.prm.A0 = int(nx_p); s.prm.A1 = 1; s.prm.B = int(zc);
+            s.prm.in = single_view(eptr(slotp(D2, me), z0, es), (long long)(ny * nzc), 0, (long long)nzc);
+            s.prm.out = s.prm.in;  // in place
+            s.stream = 2;
+            s.record = ev_yi[c] = nev++;
+            sc.steps.push_back(s);
+        }
+        Step s;
+        const PassKind zkind = c2c ? PASS_C2C_CONTIG : PASS_C2R;
+        const long long zpitch = c2c ? (long long)g.nz : (long long)(g.nz / 2);
+        rc = new_pass(zkind, c2c ? g.nz : g.nz / 2, c2c ? "z pass" : "z pass (C2R)", s);
+        if (rc) return rc;
+        s.prm.A0 = int(nx_p); s.prm.A1 = int(ny);
+        s.prm.in = single_view(slotp(D2, me), (long long)(ny * nzc), (long long)nzc, 1);
+        s.prm.out = single_view(nullptr, zpitch * (long long)ny, zpitch, 1);
+        s.out_user = 2;
+        s.stream = 0;
+        for (size_t c = 0; c < NS; ++c) s.waits.push_back(ev_yi[c]);
+        sc.steps.push_back(s);
+    }
+    sc.nevents = nev;
+    sc.built = true;
+    return DFFT_SUCCESS;
+}
+
+}  // namespace dfft
+
 // =====================================================================================================
 // memory / peer mapping
 // =====================================================================================================
@@ -790,8 +985,9 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
     int launches = 0;
     int ev = 0;
     const bool timing = p->timing;
+    cudaStream_t streams[3] = {st, p->aux[0], p->aux[1]};
     auto mark = [&](const char* name, int is_fft, const char* label = "") -> cudaError_t {
-        if (!timing) return cudaSuccess;
+        if (!timing || (sc.overlapped && is_fft != -1)) return cudaSuccess;  // overlapped: only start / end are meaningful
         if (ev >= int(p->events.size())) {
             cudaEvent_t e;
             cudaError_t r = cudaEventCreate(&e);
@@ -806,21 +1002,35 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
         p->ev_labels[ev] = label;
         return cudaEventRecord(p->events[ev++], st);
     };
+    if (sc.overlapped) {
+        while (int(p->sync_events.size()) < sc.nevents) {
+            cudaEvent_t e;
+            CK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            p->sync_events.push_back(e);
+        }
+        CK_CUDA(cudaEventRecord(p->fork_ev, st));
+        CK_CUDA(cudaStreamWaitEvent(p->aux[0], p->fork_ev, 0));
+        CK_CUDA(cudaStreamWaitEvent(p->aux[1], p->fork_ev, 0));
+    }
     CK_CUDA(mark("start", -1));
     for (Step& s : sc.steps) {
+        cudaStream_t ss = streams[s.stream];
+        for (int w : s.waits) CK_CUDA(cudaStreamWaitEvent(ss, p->sync_events[w], 0));
         if (s.type == STEP_PASS) {
             FftParams prm = s.prm;
-            if (s.in_user == 1) prm.in.seg[0].base = const_cast<void*>(in);
-            if (s.out_user == 2) prm.out.seg[0].base = out;
-            cudaError_t e = p->prec == DFFT_F64 ? launch_pass_f64(s.log2n, s.kind, prm, st) : launch_pass_f32(s.log2n, s.kind, prm, st);
+            // views on the caller's buffers store a byte offset in seg[0].base
+            if (s.in_user == 1) prm.in.seg[0].base = (char*)const_cast<void*>(in) + (size_t)s.prm.in.seg[0].base;
+            if (s.out_user == 2) prm.out.seg[0].base = (char*)out + (size_t)s.prm.out.seg[0].base;
+            cudaError_t e = p->prec == DFFT_F64 ? launch_pass_f64(s.log2n, s.kind, prm, ss) : launch_pass_f32(s.log2n, s.kind, prm, ss);
             if (e != cudaSuccess) return fail(DFFT_ERR_CUDA, std::string("FFT pass launch failed: ") + cudaGetErrorString(e));
             ++launches;
             CK_CUDA(mark(s.phase, 1, s.label));
         } else if (s.type == STEP_RENDEZVOUS) {
             const std::vector<int>& G = p->grp[s.group];
             if (G.size() > 1) {
-                rendezvous_kernel<<<1, 32 * int((G.size() + 31) / 32), 0, st>>>(p->peer_flags_d, p->flags, p->groups_d + s.group * P, int(G.size()), me, P,
-                                                                              s.phase_id, p->epoch, p->err_d, 20000000000LL);
+                const unsigned long long ticket = ++p->ticket[s.phase_id];
+                rendezvous_kernel<<<1, 32 * int((G.size() + 31) / 32), 0, ss>>>(p->peer_flags_d, p->flags, p->groups_d + s.group * P, int(G.size()), me, P,
+                                                                              s.phase_id, ticket, p->err_d, 20000000000LL);
                 CK_CUDA(cudaGetLastError());
                 ++launches;
             }
@@ -832,18 +1042,25 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
             CK_NCCL(ncclGroupStart());
             for (size_t q = 0; q < G.size(); ++q) {
                 if (G[q] == me) continue;
-                if (s.scount[q]) CK_NCCL(ncclSend(sb + s.soff[q] * es, s.scount[q] * es, ncclChar, G[q], p->comm->nccl, st));
-                if (s.rcount[q]) CK_NCCL(ncclRecv(rb + s.roff[q] * es, s.rcount[q] * es, ncclChar, G[q], p->comm->nccl, st));
+                if (s.scount[q]) CK_NCCL(ncclSend(sb + s.soff[q] * es, s.scount[q] * es, ncclChar, G[q], p->comm->nccl, ss));
+                if (s.rcount[q]) CK_NCCL(ncclRecv(rb + s.roff[q] * es, s.rcount[q] * es, ncclChar, G[q], p->comm->nccl, ss));
             }
             CK_NCCL(ncclGroupEnd());
             for (size_t q = 0; q < G.size(); ++q)
                 if (G[q] == me && s.scount[q])
-                    CK_CUDA(cudaMemcpyAsync(rb + s.roff[q] * es, sb + s.soff[q] * es, s.scount[q] * es, cudaMemcpyDeviceToDevice, st));
+                    CK_CUDA(cudaMemcpyAsync(rb + s.roff[q] * es, sb + s.soff[q] * es, s.scount[q] * es, cudaMemcpyDeviceToDevice, ss));
             CK_CUDA(mark(s.phase, 0, s.label));
+        }
+        if (s.record >= 0) CK_CUDA(cudaEventRecord(p->sync_events[s.record], ss));
+    }
+    if (sc.overlapped) {
+        for (int a = 0; a < 2; ++a) {
+            CK_CUDA(cudaEventRecord(p->join_ev[a], p->aux[a]));
+            CK_CUDA(cudaStreamWaitEvent(st, p->join_ev[a], 0));
         }
     }
     CK_CUDA(mark("Run complete", -1));
-    p->n_events_used = ev;
+    if (timing) p->n_events_used = ev;
     p->last_launches = launches;
     p->execs++;
     return DFFT_SUCCESS;
@@ -862,7 +1079,11 @@ static int exec_common(dfft_plan_t p, void* out, const void* in, int inverse, in
     Schedule& sc = p->sched[inverse ? 1 : 0][d - 1];
     if (!sc.built) {
         g_view_error = false;
-        int rc = build_schedule(p, inverse ? 1 : 0, d, sc);
+        int rc = DFFT_SUCCESS;
+        const bool want_overlap = p->cfg.send_method == DFFT_SEND_STREAMS && d == 3 && p->P > 1 && p->g.decomp == DFFT_SLAB_ZY_THEN_X &&
+                                  p->direct2 && p->xchg_ctas >= 0;
+        if (want_overlap) rc = build_overlapped_slab(p, inverse ? 1 : 0, sc);
+        else rc = build_schedule(p, inverse ? 1 : 0, d, sc);
         if (rc) return rc;
         if (g_view_error) return fail(DFFT_ERR_STATE, "internal: segments of one view disagree on the axis stride");
     }
@@ -1073,6 +1294,20 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
     p->work_bytes = p->slot_bytes * p->nslots;
     cudaError_t ce = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { delete p; return fail(DFFT_ERR_CUDA, "cudaStreamCreate failed"); }
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
+        if (cudaStreamCreateWithPriority(&p->aux[0], cudaStreamNonBlocking, hi) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&p->aux[1], cudaStreamNonBlocking, lo) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->fork_ev, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->join_ev[0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->join_ev[1], cudaEventDisableTiming) != cudaSuccess) {
+            delete p;
+            return fail(DFFT_ERR_CUDA, "stream / event creation failed");
+        }
+        const char* e = getenv("DFFT_XCHG_CTAS");
+        p->xchg_ctas = e ? atoi(e) : 48;
+    }
     int rc = plan_setup_flags(p);
     if (rc == DFFT_SUCCESS && allocate) rc = plan_setup_memory(p, nullptr);
     if (rc != DFFT_SUCCESS) {
@@ -1112,6 +1347,12 @@ int dfft_plan_destroy(dfft_plan_t p) {
     if (p->err_d) cudaFree(p->err_d);
     p->tabs.release();
     for (cudaEvent_t e : p->events) cudaEventDestroy(e);
+    for (cudaEvent_t e : p->sync_events) cudaEventDestroy(e);
+    if (p->fork_ev) cudaEventDestroy(p->fork_ev);
+    for (int a = 0; a < 2; ++a) {
+        if (p->join_ev[a]) cudaEventDestroy(p->join_ev[a]);
+        if (p->aux[a]) cudaStreamDestroy(p->aux[a]);
+    }
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     delete p;
     return DFFT_SUCCESS;

@@ -53,6 +53,9 @@ struct FftParams {
     int inverse;      // 0 forward (e^-), 1 inverse (e^+), both unnormalised like cuFFT
     const void* tw;   // exp(-2*pi*i*m/N), m < N, N = pass length (complex length for R2C/C2R)
     const void* tw2;  // R2C/C2R only: exp(-2*pi*i*k/(2N)), k <= N/2
+    int max_ctas;     // > 0: run as a persistent kernel on at most this many CTAs (SM partitioning for the
+                      // overlapped schedule: the exchange pass keeps a few SMs, the local passes the rest)
+    int pad_;
 };
 
 enum PassKind { PASS_C2C_CONTIG = 0, PASS_C2C_TILED = 1, PASS_R2C = 2, PASS_C2R = 3 };

@@ -32,11 +32,19 @@ def main():
                     cases.append((dfft.MPIcuFFT_Slab_Z_Then_YX, None, method, prec, transform, shape))
                     for g in grids:
                         cases.append((dfft.MPIcuFFT_Pencil, g, method, prec, transform, shape))
+    # overlapped schedule (SendMethod Streams) of the slab: z | y+exchange | x passes on three streams
+    for prec in ((dfft.F64,) if quick else (dfft.F64, dfft.F32)):
+        for transform in (dfft.R2C, dfft.C2C):
+            for shape in ([(32, 16, 64)] if quick else [(32, 16, 64), (64, 64, 256), (16, 128, 8), (256, 64, 128)]):
+                cases.append((dfft.MPIcuFFT_Slab, "streams", dfft.CommunicationMethod.Peer2Peer, prec, transform, shape))
     fails = 0
     for cls, grid, method, prec, transform, shape in cases:
+        streams = grid == "streams"
+        if streams:
+            grid = None
         f64 = prec == dfft.F64
         tol = 1e-10 if f64 else 1e-5
-        cfg = dfft.Configurations(comm_method=method, comm_method2=method)
+        cfg = dfft.Configurations(comm_method=method, comm_method2=method, send_method=dfft.SendMethod.Streams if streams else dfft.SendMethod.Sync)
         plan = cls(cfg, comm, precision="double" if f64 else "float", transform="c2c" if transform == dfft.C2C else "r2c")
         part = dfft.Pencil_Partition(*grid) if grid else None
         plan.initFFT(dfft.GlobalSize(*shape), part, True)
@@ -77,7 +85,7 @@ def main():
         e = torch.tensor([max(errs), eb, 0.0 if ok else 1.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(e, op=dist.ReduceOp.MAX)
         if rank == 0:
-            name = cls.__name__ + (f"{grid[0]}x{grid[1]}" if grid else "")
+            name = cls.__name__ + (f"{grid[0]}x{grid[1]}" if grid else "") + ("/Streams" if streams else "")
             print(f"{'ok  ' if e[2] == 0 else 'FAIL'} {name:34s} {method.name:9s} {'f64' if f64 else 'f32'} {'c2c' if c2c else 'r2c'} "
                   f"{shape} fwd={e[0].item():.2e} inv={e[1].item():.2e}", flush=True)
         fails += int(e[2].item())
