@@ -4,6 +4,6 @@ stores); this package is the thin host-side mirror of the reference's classes ov
 from .params import (CommunicationMethod, Configurations, GlobalSize, Partition, Pencil_Partition, SendMethod,
                      Slab_Partition, partition_sizes)
 from .mpicufft import (C2C, F32, F64, FORWARD, INVERSE, PENCIL, R2C, SLAB_Z_THEN_YX, SLAB_ZY_THEN_X, Comm, MPIcuFFT,
-                       MPIcuFFT_Pencil, MPIcuFFT_Slab, MPIcuFFT_Slab_Z_Then_YX, fft1d_contig, fft1d_strided, layout)
+                       MPIcuFFT_Pencil, MPIcuFFT_Slab, MPIcuFFT_Slab_Z_Then_YX, fft1d_contig, fft1d_general, fft1d_strided, layout)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -1572,4 +1572,24 @@ int dfft_fft1d_strided(int precision, int direction, size_t a, size_t n, size_t 
     return DFFT_SUCCESS;
 }
 
+int dfft_fft1d_general(int precision, int direction, size_t n, size_t a0, size_t a1, size_t b, void* out, const long long out_strides[3],
+                       const void* in, const long long in_strides[3], void* stream) {
+    if (precision != DFFT_F32 && precision != DFFT_F64) return fail(DFFT_ERR_INVALID, "bad precision");
+    const int l2 = ilog2_exact(n);
+    if (l2 < 1 || l2 > MAX_LOG2N) return fail(DFFT_ERR_UNSUPPORTED, "length must be a power of two");
+    FftParams prm{};
+    prm.A0 = int(a0); prm.A1 = int(a1); prm.B = int(b);
+    prm.inverse = direction > 0 ? 1 : 0;
+    void* tw = nullptr;
+    int rc = cached_table(false, precision, l2, &tw);
+    if (rc) return rc;
+    prm.tw = tw;
+    prm.in = single_view(const_cast<void*>(in), in_strides[0], in_strides[1], in_strides[2]);
+    prm.out = single_view(out, out_strides[0], out_strides[1], out_strides[2]);
+    cudaError_t e = precision == DFFT_F64 ? launch_pass_f64(l2, PASS_C2C_TILED, prm, (cudaStream_t)stream)
+                                          : launch_pass_f32(l2, PASS_C2C_TILED, prm, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(DFFT_ERR_CUDA, std::string("launch failed: ") + cudaGetErrorString(e));
+    return DFFT_SUCCESS;
+}
+
 }  // extern "C"

@@ -57,21 +57,21 @@ static cudaError_t launch_tiled(const FftParams& p, cudaStream_t stream, long lo
     const long long grid = lines * ((p.B + TB - 1) / TB);
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     if constexpr (C::THREADS <= (sizeof(T) == 8 ? 256 : 512)) {
-        if (pipe_mode() || p.max_ctas > 0) {
+        if (pipe_mode() && p.max_ctas <= 0) {
             auto pf = fft_c2c_pipe_kernel<T, LOG2N, LOG2E, TB, true, false>;
             auto pi = fft_c2c_pipe_kernel<T, LOG2N, LOG2E, TB, true, true>;
             static cudaError_t oncep = set_smem(pf, C::SMEM_BYTES) != cudaSuccess ? cudaErrorInvalidValue : set_smem(pi, C::SMEM_BYTES);
             if (oncep != cudaSuccess) return oncep;
-            static int ctas_all = persistent_ctas(pf, C::THREADS, C::SMEM_BYTES);
-            const int ctas = (p.max_ctas > 0 && p.max_ctas < ctas_all) ? p.max_ctas : ctas_all;
+            static int ctas = persistent_ctas(pf, C::THREADS, C::SMEM_BYTES);
             const unsigned g = unsigned(grid < ctas ? grid : ctas);
             if (p.inverse) pi<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
             else pf<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
             return cudaGetLastError();
         }
     }
-    if (p.inverse) ki<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
-    else kf<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
+    const unsigned g = unsigned((p.max_ctas > 0 && grid > p.max_ctas) ? p.max_ctas : grid);
+    if (p.inverse) ki<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
+    else kf<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
 }
 

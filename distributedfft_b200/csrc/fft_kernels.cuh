@@ -227,87 +227,101 @@ struct TileCoord {
 };
 
 // ---- C2C pass ------------------------------------------------------------------------------------------
+// Grid-stride over tiles: launched with one CTA per tile it is the plain kernel; launched with fewer CTAs
+// (FftParams::max_ctas) it is persistent and occupies only that many CTA slots, which is how the overlapped
+// schedule leaves the rest of the GPU to the other passes.
 template <typename T, int LOG2N, int LOG2E, int TB, bool TILED, bool INV>
 __global__ void __launch_bounds__((1 << (LOG2N - LOG2E)) * TB)
 fft_c2c_kernel(const __grid_constant__ FftParams p) {
     using C = CtaFft<T, LOG2N, LOG2E, TB, TILED>;
     using LA = LineAccess<T, C::LINES>;
+    using TC = TileCoord<C, TILED, TB>;
     constexpr int E = C::E, TPL = C::TPL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
     unsigned long long* tab_in = reinterpret_cast<unsigned long long*>(smem_raw + C::TILE_BYTES);
     unsigned long long* tab_out = tab_in + C::LINES * MAXSEG;
-
-    const TileCoord<C, TILED, TB> tc(p);
-    const int j = tc.j, t = tc.t;
     const bool multi = p.in.nseg > 1 || p.out.nseg > 1;
-    if (multi) {
-        // TILED: one table per CTA (a0, a1 are CTA-uniform), filled by the first threads;
-        // CONTIG: one table per line, filled by that line's threads.
-        const int line = TILED ? 0 : t;
-        const int lane = TILED ? int(threadIdx.x) : j;
-        const int lanes = TILED ? C::THREADS : TPL;
-        LA::fill_table(p.in, tab_in, line, lane, lanes, tc.a0, tc.a1);
-        LA::fill_table(p.out, tab_out, line, lane, lanes, tc.a0, tc.a1);
-        __syncthreads();
-    }
-    const LA in(p.in, tab_in, TILED ? 0 : t, tc.a0, tc.a1, tc.b);
-    const LA out(p.out, tab_out, TILED ? 0 : t, tc.a0, tc.a1, tc.b);
+    const long long ntiles = TC::num_tiles(p);
 
-    cx<T> v[E];
-    if (tc.valid) {
-        if (!in.multi) {
-            if constexpr (!TILED) {
-                // contiguous line: sN == 1, immediate offsets
-                const cx<T>* q = in.p0 + j;
+#pragma unroll 1
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TC tc(p, tile);
+        const int j = tc.j, t = tc.t;
+        if (multi) {
+            // TILED: one table per CTA (a0, a1 are CTA-uniform), filled by the first threads;
+            // CONTIG: one table per line, filled by that line's threads.
+            const int line = TILED ? 0 : t;
+            const int lane = TILED ? int(threadIdx.x) : j;
+            const int lanes = TILED ? C::THREADS : TPL;
+            LA::fill_table(p.in, tab_in, line, lane, lanes, tc.a0, tc.a1);
+            LA::fill_table(p.out, tab_out, line, lane, lanes, tc.a0, tc.a1);
+            __syncthreads();
+        }
+        const LA in(p.in, tab_in, TILED ? 0 : t, tc.a0, tc.a1, tc.b);
+        const LA out(p.out, tab_out, TILED ? 0 : t, tc.a0, tc.a1, tc.b);
+
+        cx<T> v[E];
+        if (tc.valid) {
+            if (!in.multi) {
+                if constexpr (!TILED) {
+                    // contiguous line: sN == 1, immediate offsets
+                    const cx<T>* q = in.p0 + j;
 #pragma unroll
-                for (int e = 0; e < E; ++e) v[e] = ld_elem<T>(q + e * TPL);
+                    for (int e = 0; e < E; ++e) v[e] = ld_elem<T>(q + e * TPL);
+                } else {
+                    const long long step = (long long)TPL * p.in.sN;
+                    const cx<T>* q = in.p0 + (long long)j * p.in.sN;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) { v[e] = ld_elem<T>(q); q += step; }
+                }
             } else {
-                const long long step = (long long)TPL * p.in.sN;
-                const cx<T>* q = in.p0 + (long long)j * p.in.sN;
 #pragma unroll
-                for (int e = 0; e < E; ++e) { v[e] = ld_elem<T>(q); q += step; }
+                for (int e = 0; e < E; ++e) v[e] = ld_elem<T>(in.at(j + e * TPL));
+            }
+            if constexpr (INV) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = cswap(v[e]);
             }
         } else {
 #pragma unroll
-            for (int e = 0; e < E; ++e) v[e] = ld_elem<T>(in.at(j + e * TPL));
+            for (int e = 0; e < E; ++e) v[e] = cx<T>{T(0), T(0)};
         }
-        if constexpr (INV) {
-#pragma unroll
-            for (int e = 0; e < E; ++e) v[e] = cswap(v[e]);
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = cx<T>{T(0), T(0)};
-    }
 
-    C::template stages<0>(v, j, t, sm, reinterpret_cast<const cx<T>*>(p.tw));
+        C::template stages<0>(v, j, t, sm, reinterpret_cast<const cx<T>*>(p.tw));
 
-    if (tc.valid) {
-        if (!out.multi) {
-            if constexpr (!TILED) {
-                cx<T>* q = out.p0 + j;
+        if (tc.valid) {
+            if (!out.multi) {
+                if constexpr (!TILED) {
+                    cx<T>* q = out.p0 + j;
 #pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const cx<T> x = v[C::Core::final_slot(e)];
-                    st_elem<T>(q + e * TPL, INV ? cswap(x) : x);
+                    for (int e = 0; e < E; ++e) {
+                        const cx<T> x = v[C::Core::final_slot(e)];
+                        st_elem<T>(q + e * TPL, INV ? cswap(x) : x);
+                    }
+                } else {
+                    const long long step = (long long)TPL * p.out.sN;
+                    cx<T>* q = out.p0 + (long long)j * p.out.sN;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const cx<T> x = v[C::Core::final_slot(e)];
+                        st_elem<T>(q, INV ? cswap(x) : x);
+                        q += step;
+                    }
                 }
             } else {
-                const long long step = (long long)TPL * p.out.sN;
-                cx<T>* q = out.p0 + (long long)j * p.out.sN;
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const cx<T> x = v[C::Core::final_slot(e)];
-                    st_elem<T>(q, INV ? cswap(x) : x);
-                    q += step;
+                    st_elem<T>(out.at(j + e * TPL), INV ? cswap(x) : x);
                 }
             }
-        } else {
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const cx<T> x = v[C::Core::final_slot(e)];
-                st_elem<T>(out.at(j + e * TPL), INV ? cswap(x) : x);
-            }
+        }
+        if (tile + gridDim.x < ntiles) {
+            // persistent use: the next tile's first scatter must not overtake this tile's last gather, and
+            // the segment tables are rewritten
+            if (multi) __syncthreads();
+            else if constexpr (C::NST > 1) C::sync(t);
         }
     }
 }

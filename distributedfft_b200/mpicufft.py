@@ -258,3 +258,10 @@ def fft1d_contig(precision: int, kind: int, direction: int, n: int, lines: int, 
 
 def fft1d_strided(precision: int, direction: int, a: int, n: int, b: int, out, in_, stream=None):
     check(lib().dfft_fft1d_strided(precision, direction, a, n, b, _ptr(out), _ptr(in_), _stream_ptr(stream)))
+
+
+def fft1d_general(precision: int, direction: int, n: int, a0: int, a1: int, b: int, out, out_strides, in_, in_strides, stream=None):
+    """Batched C2C along n over a general view: element (i0,i1,n,ib) at i0*s[0] + i1*s[1] + n*s[2] + ib."""
+    os_ = (C.c_longlong * 3)(*out_strides)
+    is_ = (C.c_longlong * 3)(*in_strides)
+    check(lib().dfft_fft1d_general(precision, direction, n, a0, a1, b, _ptr(out), os_, _ptr(in_), is_, _stream_ptr(stream)))

@@ -185,6 +185,11 @@ int dfft_fft1d_contig(int precision, int kind, int direction, size_t n, size_t l
 int dfft_fft1d_strided(int precision, int direction, size_t a, size_t n, size_t b, void* out, const void* in,
                        void* stream);
 
+/* Batched 1D C2C along n of element (i0, i1, n, ib) at  i0*strides[0] + i1*strides[1] + n*strides[2] + ib
+ * (elements; ib contiguous, extents a0 x a1 x n x b) — the general strided view the plan's passes use. */
+int dfft_fft1d_general(int precision, int direction, size_t n, size_t a0, size_t a1, size_t b, void* out,
+                       const long long out_strides[3], const void* in, const long long in_strides[3], void* stream);
+
 #ifdef __cplusplus
 }
 #endif
