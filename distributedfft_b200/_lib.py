@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdfft.so")
+LIB_PATH = os.environ.get("DFFT_LIB") or os.path.join(_HERE, "libdfft.so")  # DFFT_LIB: experimental build variants
 
 UNIQUE_ID_BYTES = 128
 

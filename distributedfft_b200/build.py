@@ -50,19 +50,22 @@ def _compile(src, obj, defs, deps, verbose):
     return obj
 
 
-def build(verbose: bool = False, force: bool = False) -> str:
-    os.makedirs(OBJ, exist_ok=True)
+def build(verbose: bool = False, force: bool = False, defines=(), out: str = LIB, objdir: str = OBJ) -> str:
+    """defines / out / objdir: experimental variants (e.g. build(defines=["-DDFFT_CONTIG_THREADS=128"],
+    out=".../libdfft_t128.so", objdir=".../build_t128"); select at run time with DFFT_LIB=<path>)."""
+    OBJ_ = objdir
+    os.makedirs(OBJ_, exist_ok=True)
     headers = [os.path.join(CSRC, h) for h in ("fft_core.cuh", "fft_kernels.cuh", "geometry.hpp")]
     headers.append(os.path.join(HERE, "..", "include", "dfft.h"))
     jobs = []
     inst = os.path.join(CSRC, "fft_inst.cu")
     for tname in ("double", "float"):
         for l in range(1, MAX_LOG2N + 1):
-            obj = os.path.join(OBJ, f"fft_inst_{tname}_{l}.o")
-            jobs.append((inst, obj, [f"-DDFFT_T={tname}", f"-DDFFT_LOG2N={l}"], [inst, *headers]))
+            obj = os.path.join(OBJ_, f"fft_inst_{tname}_{l}.o")
+            jobs.append((inst, obj, [f"-DDFFT_T={tname}", f"-DDFFT_LOG2N={l}", *defines], [inst, *headers]))
     for name in ("fft_dispatch.cu", "dfft_plan.cu"):
         src = os.path.join(CSRC, name)
-        jobs.append((src, os.path.join(OBJ, name.replace(".cu", ".o")), [], [src, *headers]))
+        jobs.append((src, os.path.join(OBJ_, name.replace(".cu", ".o")), list(defines), [src, *headers]))
     if force:
         for _, obj, _, _ in jobs:
             if os.path.exists(obj + ".stamp"):
@@ -74,13 +77,13 @@ def build(verbose: bool = False, force: bool = False) -> str:
         for f in futs:
             objs.append(f.result())
     lstamp = _stamp(objs)
-    lfile = LIB + ".stamp"
-    if not (os.path.exists(LIB) and os.path.exists(lfile) and open(lfile).read() == lstamp):
-        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lnccl", "-Xlinker", "-z,noexecstack"]
+    lfile = out + ".stamp"
+    if not (os.path.exists(out) and os.path.exists(lfile) and open(lfile).read() == lstamp):
+        cmd = [NVCC, *ARCH, "-shared", "-o", out, *objs, "-lnccl", "-Xlinker", "-z,noexecstack"]
         _run(cmd)
         with open(lfile, "w") as f:
             f.write(lstamp)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -66,8 +66,11 @@ struct Shape {
     static constexpr int LOG2E = LOG2N < 4 ? LOG2N : 4;
     static constexpr int N = 1 << LOG2N;
     static constexpr int TPL = N >> LOG2E;
-    // CONTIG: lines per CTA, aim at 256 threads
-    static constexpr int TBC = (256 / TPL) < 1 ? 1 : ((256 / TPL) > 64 ? 64 : (256 / TPL));
+    // CONTIG: lines per CTA, aim at DFFT_CONTIG_THREADS threads
+#ifndef DFFT_CONTIG_THREADS
+#define DFFT_CONTIG_THREADS 256
+#endif
+    static constexpr int TBC = (DFFT_CONTIG_THREADS / TPL) < 1 ? 1 : ((DFFT_CONTIG_THREADS / TPL) > 64 ? 64 : (DFFT_CONTIG_THREADS / TPL));
     // TILED: tile width; rows of >= 64 bytes where shared memory allows, 4096 (f64) / 8192 (f32) points
     static constexpr int MINROW = 64 / int(2 * sizeof(T));
     static constexpr int WANT = (sizeof(T) == 8 ? 4096 : 8192) / N;
