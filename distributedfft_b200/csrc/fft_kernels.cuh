@@ -66,11 +66,15 @@ struct Shape {
     static constexpr int LOG2E = LOG2N < 4 ? LOG2N : 4;
     static constexpr int N = 1 << LOG2N;
     static constexpr int TPL = N >> LOG2E;
-    // CONTIG: lines per CTA, aim at DFFT_CONTIG_THREADS threads
-#ifndef DFFT_CONTIG_THREADS
-#define DFFT_CONTIG_THREADS 256
+    // CONTIG: lines per CTA.  Measured on B200 (tools/axis_bench.py): f64 lines of >= 512 points run 6-9 % faster
+    // with 128-thread CTAs (four CTAs per SM interleave their load / compute / store phases), short lines
+    // and f32 prefer 256 threads.  -DDFFT_CONTIG_THREADS=<n> overrides for experiments.
+#ifdef DFFT_CONTIG_THREADS
+    static constexpr int CT = DFFT_CONTIG_THREADS;
+#else
+    static constexpr int CT = (sizeof(T) == 8 && LOG2N >= 9) ? 128 : 256;
 #endif
-    static constexpr int TBC = (DFFT_CONTIG_THREADS / TPL) < 1 ? 1 : ((DFFT_CONTIG_THREADS / TPL) > 64 ? 64 : (DFFT_CONTIG_THREADS / TPL));
+    static constexpr int TBC = (CT / TPL) < 1 ? 1 : ((CT / TPL) > 64 ? 64 : (CT / TPL));
     // TILED: tile width; rows of >= 64 bytes where shared memory allows, 4096 (f64) / 8192 (f32) points
     static constexpr int MINROW = 64 / int(2 * sizeof(T));
     static constexpr int WANT = (sizeof(T) == 8 ? 4096 : 8192) / N;
