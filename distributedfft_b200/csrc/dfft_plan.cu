@@ -1306,7 +1306,7 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
             return fail(DFFT_ERR_CUDA, "stream / event creation failed");
         }
         const char* e = getenv("DFFT_XCHG_CTAS");
-        p->xchg_ctas = e ? atoi(e) : 48;
+        p->xchg_ctas = e ? atoi(e) : 128;
     }
     int rc = plan_setup_flags(p);
     if (rc == DFFT_SUCCESS && allocate) rc = plan_setup_memory(p, nullptr);
