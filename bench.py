@@ -163,7 +163,7 @@ def run_reference(args, shape):
     print(json.dumps(line), flush=True)
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -179,7 +179,7 @@ def main():
     ap.add_argument("--transform", default="c2c", choices=["c2c", "r2c"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     args.warmup = max(args.warmup, 3) if args.impl == "dfft" else args.warmup
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -200,8 +200,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if world > 1:
+    own_pg = False
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        own_pg = True
     comm = dfft.Comm.from_torch_distributed(local)
     f64 = args.prec == "f64"
     cdt = torch.complex128 if f64 else torch.complex64
@@ -396,7 +398,10 @@ def main():
         }
         print(json.dumps(line), flush=True)
     plan.destroy()
-    if world > 1:
+    comm.destroy()
+    del x, out
+    torch.cuda.empty_cache()
+    if own_pg:
         dist.destroy_process_group()
 
 

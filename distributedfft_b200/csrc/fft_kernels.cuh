@@ -75,9 +75,19 @@ struct Shape {
     static constexpr int CT = (sizeof(T) == 8 && LOG2N >= 9) ? 128 : 256;
 #endif
     static constexpr int TBC = (CT / TPL) < 1 ? 1 : ((CT / TPL) > 64 ? 64 : (CT / TPL));
-    // TILED: tile width; rows of >= 64 bytes where shared memory allows, 4096 (f64) / 8192 (f32) points
-    static constexpr int MINROW = 64 / int(2 * sizeof(T));
-    static constexpr int WANT = (sizeof(T) == 8 ? 4096 : 8192) / N;
+    // TILED: tile width; rows of >= DFFT_MINROW_BYTES where shared memory allows, DFFT_TILE_POINTS_F64 / _F32
+    // points per tile (experiment knobs; defaults measured best on B200)
+#ifndef DFFT_MINROW_BYTES
+#define DFFT_MINROW_BYTES 64
+#endif
+#ifndef DFFT_TILE_POINTS_F64
+#define DFFT_TILE_POINTS_F64 4096
+#endif
+#ifndef DFFT_TILE_POINTS_F32
+#define DFFT_TILE_POINTS_F32 8192
+#endif
+    static constexpr int MINROW = DFFT_MINROW_BYTES / int(2 * sizeof(T));
+    static constexpr int WANT = (sizeof(T) == 8 ? DFFT_TILE_POINTS_F64 : DFFT_TILE_POINTS_F32) / N;
     static constexpr int TBT_ = WANT < MINROW ? MINROW : (WANT > 32 ? 32 : WANT);
     // keep the tile within 128 KB of shared memory and 1024 threads
     static constexpr int CAP1 = (128 * 1024) / (N * int(2 * sizeof(T)));
@@ -137,6 +147,12 @@ struct LineAccess {
         if (!multi) return p0 + (long long)n * v.sN;
         const int s = v.seg_of_n[n];
         return reinterpret_cast<cx<T>*>(tab[s]) + ((long long)n * v.sN + boff);
+    }
+    // unit stride along n (every CONTIG view): no multiply
+    __device__ __forceinline__ cx<T>* at1(int n) const {
+        if (!multi) return p0 + n;
+        const int s = v.seg_of_n[n];
+        return reinterpret_cast<cx<T>*>(tab[s]) + (n + boff);
     }
 };
 
@@ -284,7 +300,7 @@ fft_c2c_kernel(const __grid_constant__ FftParams p) {
                 }
             } else {
 #pragma unroll
-                for (int e = 0; e < E; ++e) v[e] = ld_elem<T>(in.at(j + e * TPL));
+                for (int e = 0; e < E; ++e) v[e] = ld_elem<T>(TILED ? in.at(j + e * TPL) : in.at1(j + e * TPL));
             }
             if constexpr (INV) {
 #pragma unroll
@@ -320,7 +336,7 @@ fft_c2c_kernel(const __grid_constant__ FftParams p) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const cx<T> x = v[C::Core::final_slot(e)];
-                    st_elem<T>(out.at(j + e * TPL), INV ? cswap(x) : x);
+                    st_elem<T>(TILED ? out.at(j + e * TPL) : out.at1(j + e * TPL), INV ? cswap(x) : x);
                 }
             }
         }
@@ -481,8 +497,8 @@ fft_r2c_kernel(const __grid_constant__ FftParams p) {
         const cx<T> xo = cx<T>{T(0.5) * d.y, T(-0.5) * d.x};  // -i/2 * d
         const cx<T> tt = cmul(ld_tw(tw2, k), xo);
         if (valid) {
-            st_elem<T>(out.at(k), cadd(xe, tt));
-            st_elem<T>(out.at(M - k), cconj(csub(xe, tt)));
+            st_elem<T>(out.at1(k), cadd(xe, tt));
+            st_elem<T>(out.at1(M - k), cconj(csub(xe, tt)));
         }
     };
 #pragma unroll
@@ -516,8 +532,8 @@ fft_c2r_kernel(const __grid_constant__ FftParams p) {
     auto build = [&](int k) {
         cx<T> xk{T(0), T(0)}, xm{T(0), T(0)};
         if (valid) {
-            xk = ld_elem<T>(in.at(k));
-            xm = cconj(ld_elem<T>(in.at(M - k)));
+            xk = ld_elem<T>(in.at1(k));
+            xm = cconj(ld_elem<T>(in.at1(M - k)));
         }
         const cx<T> xe = cadd(xk, xm);
         const cx<T> xo = cmul(cconj(ld_tw(tw2, k)), csub(xk, xm));

@@ -1,0 +1,195 @@
+#!/usr/bin/env python
+"""Command-line drivers with the reference's flags: the `slab` and `pencil` executables of
+/root/reference/tests/src/slab/main.cpp:26-60,120-169 and tests/src/pencil/main.cpp:147-192, testcases 0-4
+(tests/src/slab/random_dist_default.cu:152-758), driving the new library through its reference-shaped API.
+
+    python tests/cli.py slab -nx 256 -ny 256 -nz 256 -t 1 -d                       # one GPU
+    torchrun --nproc-per-node 4 tests/cli.py slab -nx 256 -ny 256 -nz 256 -s Z_Then_YX -snd Streams -i 10 -d -b ./bench
+    torchrun --nproc-per-node 8 tests/cli.py pencil -nx 256 -ny 256 -nz 256 -p1 2 -p2 4 -t 4 -d
+
+`mpirun -n P` becomes `torchrun --nproc-per-node P`; `-c/--cuda_aware` is accepted (buffers are always device
+memory); `-o/--opt` is accepted and ignored (the transposing stores of the Opt1 classes are always fused into the
+FFT passes).  Unlike the reference every testcase has a tolerance and an exit code.
+This file is test infrastructure: testcases 1 and 4 check against oracle/dft_oracle.py.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import distributedfft_b200 as dfft  # noqa: E402
+from oracle import dft_oracle as O  # noqa: E402
+
+
+def parse(argv):
+    ap = argparse.ArgumentParser(prog="cli.py", description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("program", choices=["slab", "pencil"])
+    ap.add_argument("-nx", "--input-dim-x", dest="nx", type=int, required=True)
+    ap.add_argument("-ny", "--input-dim-y", dest="ny", type=int, required=True)
+    ap.add_argument("-nz", "--input-dim-z", dest="nz", type=int, required=True)
+    ap.add_argument("-s", "--sequence", default="ZY_Then_X", choices=["ZY_Then_X", "Z_Then_YX"])
+    ap.add_argument("-comm", "--comm-method", dest="comm", default="Peer2Peer", choices=["Peer2Peer", "All2All"])
+    ap.add_argument("-snd", "--send-method", dest="snd", default="Sync", choices=["Sync", "Streams", "MPI_Type"])
+    ap.add_argument("-comm2", "--comm-method2", dest="comm2", default=None, choices=["Peer2Peer", "All2All"])
+    ap.add_argument("-snd2", "--send-method2", dest="snd2", default=None, choices=["Sync", "Streams", "MPI_Type"])
+    ap.add_argument("-p1", "--partition1", dest="p1", type=int, default=0)
+    ap.add_argument("-p2", "--partition2", dest="p2", type=int, default=0)
+    ap.add_argument("-t", "--testcase", type=int, default=0, choices=[0, 1, 2, 3, 4])
+    ap.add_argument("-f", "--fft-dim", dest="fft_dim", type=int, default=3, choices=[1, 2, 3], help="pencil: transform only the first f dimensions")
+    ap.add_argument("-o", "--opt", type=int, default=0, choices=[0, 1])
+    ap.add_argument("-i", "--iterations", type=int, default=0)
+    ap.add_argument("-w", "--warmup-rounds", dest="warmup", type=int, default=0)
+    ap.add_argument("-c", "--cuda_aware", action="store_true")
+    ap.add_argument("-d", "--double_prec", action="store_true")
+    ap.add_argument("-b", "--benchmark_dir", default="")
+    a = ap.parse_args(argv)
+    if a.iterations == 0 and a.warmup == 0:
+        a.iterations = 1
+    a.iterations += a.warmup
+    return a
+
+
+def main(argv=None):
+    a = parse(argv if argv is not None else sys.argv[1:])
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = dfft.Comm.from_torch_distributed(local)
+    CM, SM = dfft.CommunicationMethod, dfft.SendMethod
+    cfg = dfft.Configurations(cuda_aware=a.cuda_aware, warmup_rounds=a.warmup, comm_method=CM[a.comm], send_method=SM[a.snd],
+                              benchmark_dir=a.benchmark_dir, comm_method2=CM[a.comm2 or a.comm], send_method2=SM[a.snd2 or a.snd])
+    prec = "double" if a.double_prec else "float"
+    f64 = a.double_prec
+    if a.program == "pencil":
+        p1 = a.p1 or 1
+        p2 = a.p2 or world // p1
+        plan = dfft.MPIcuFFT_Pencil(cfg, comm, precision=prec)
+        plan.initFFT(dfft.GlobalSize(a.nx, a.ny, a.nz), dfft.Pencil_Partition(p1, p2), True)
+    else:
+        cls = dfft.MPIcuFFT_Slab if a.sequence == "ZY_Then_X" else dfft.MPIcuFFT_Slab_Z_Then_YX
+        plan = cls(cfg, comm, precision=prec)
+        plan.initFFT(dfft.GlobalSize(a.nx, a.ny, a.nz), None, True)
+    shape = (a.nx, a.ny, a.nz)
+    d = a.fft_dim if a.program == "pencil" else 3
+    isz, ist = plan.getInSize(), plan.getInStart()
+    osz, ost = (plan.getOutSize(), plan.getOutStart()) if d == 3 else (plan.getPartialSize(d), plan.getPartialStart(d))
+    rdt = torch.float64 if f64 else torch.float32
+    cdt = torch.complex128 if f64 else torch.complex64
+    npr = np.float64 if f64 else np.float32
+    tol = 1e-10 if f64 else 1e-5
+    dom = plan.getDomainSize() // (16 if f64 else 8)
+    n_out = osz[0] * osz[1] * osz[2]
+    out = torch.empty(dom, dtype=cdt, device="cuda")
+    small = a.nx * a.ny * a.nz <= 256 ** 3
+    status = 0
+
+    def allmax(v):
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for it in range(a.iterations):
+            barrier()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            ms = allmax((time.perf_counter() - t0) * 1e3)
+            if rank == 0 and it >= a.warmup:
+                print(f"Run complete: {ms:.4f} ms")
+
+    if a.testcase in (0, 2):
+        g = torch.Generator(device="cuda").manual_seed(1 + rank)
+        if a.testcase == 0:
+            x = torch.rand(isz, generator=g, device="cuda", dtype=rdt) * 255
+            timed(lambda: plan.execR2C(out, x, d))
+        else:
+            spec = torch.complex(torch.rand(n_out, generator=g, device="cuda", dtype=rdt), torch.rand(n_out, generator=g, device="cuda", dtype=rdt))
+            buf = torch.zeros(dom, dtype=cdt, device="cuda"); buf[:n_out] = spec
+            back = torch.empty(isz, dtype=rdt, device="cuda")
+            timed(lambda: plan.execC2R(back, buf, d))
+    elif a.testcase == 1:
+        # distributed result == single 3D transform (the reference's coordinator runs cufftPlan3d; here the oracle)
+        if not small:
+            raise SystemExit("testcase 1 keeps the global array on every rank: use sizes up to 256^3")
+        xg = O.real_input(shape, dtype=npr)
+        ref = O.fft_r2c(xg, d)
+        x = torch.from_numpy(np.ascontiguousarray(O.block(xg, ist, isz))).cuda()
+        for _ in range(a.iterations):
+            plan.execR2C(out, x, d)
+        got = out[:n_out].cpu().numpy().reshape(osz)
+        blk = O.block(ref, ost, osz)
+        l1 = float(np.abs((got - blk).real).sum() + np.abs((got - blk).imag).sum())
+        rel = allmax(O.rel_l2(got, blk))
+        if rank == 0:
+            print(f"Result {l1}")
+            print(f"Result (relative L2, max over ranks): {rel:.3e}  tolerance {tol:g}")
+        status = int(rel >= tol)
+    elif a.testcase == 3:
+        if small:
+            x = torch.from_numpy(O.real_input(shape, ist, isz, dtype=npr)).cuda()
+        else:
+            x = torch.rand(isz, generator=torch.Generator(device="cuda").manual_seed(1 + rank), device="cuda", dtype=rdt) * 255
+        back = torch.empty_like(x)
+        scale = float(a.nz * (a.ny if d >= 2 else 1) * (a.nx if d >= 3 else 1))
+        for _ in range(a.iterations):
+            plan.execR2C(out, x, d)
+            plan.execC2R(back, out, d)
+        err = (back - x * scale).abs()
+        s = torch.stack([err.sum(), torch.tensor(float(err.numel()), device="cuda", dtype=err.dtype)]).double()
+        if world > 1:
+            dist.all_reduce(s)
+        mx = allmax(float(err.max()))
+        rel = mx / (255.0 * scale)
+        if rank == 0:
+            print(f"Result (avg): {float(s[0] / s[1])}")
+            print(f"Result (max): {mx}")
+            print(f"Result (max, relative to 255*N): {rel:.3e}  tolerance {tol:g}")
+        status = int(rel >= tol)
+    else:
+        # spectral Laplacian of sin*sin*sin against -3 sqrt(N) f (random_dist_default.cu:625-758)
+        if d != 3:
+            raise SystemExit("testcase 4 needs the full transform")
+        f = torch.from_numpy(O.sine_input(shape, ist, isz, dtype=npr)).cuda()
+        coeff = torch.from_numpy(O.laplacian_coefficients(a.nx, a.ny, a.nz, ost, osz).astype(npr)).cuda().reshape(-1)
+        back = torch.empty_like(f)
+        for _ in range(a.iterations):
+            plan.execR2C(out, f)
+            out[:n_out] *= coeff
+            plan.execC2R(back, out)
+        expect = torch.from_numpy(O.laplacian_expected(shape, ist, isz).astype(npr)).cuda()
+        err = (back - expect).abs()
+        s = torch.stack([err.sum(), torch.tensor(float(err.numel()), device="cuda", dtype=err.dtype)]).double()
+        if world > 1:
+            dist.all_reduce(s)
+        mx = allmax(float(err.max()))
+        amp = 3.0 * np.sqrt(float(a.nx) * a.ny * a.nz)
+        rel = mx / amp
+        if rank == 0:
+            print(f"Result (avg): {float(s[0] / s[1])}")
+            print(f"Result (max): {mx}")
+            print(f"Result (max, relative to 3*sqrt(N)): {rel:.3e}  tolerance {max(tol, 1e-12):g}")
+        status = int(rel >= tol)
+    plan.destroy()
+    if world > 1:
+        dist.destroy_process_group()
+    return status
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -180,3 +180,22 @@ def test_timer_csv_schema(tmp_path):
     steps = plan.stepTimes()
     assert [l for l, _ in steps] == ["z pass (R2C)", "y pass", "x pass"]
     plan.destroy()
+
+
+@pytest.mark.parametrize("argv", [
+    ["slab", "-nx", "64", "-ny", "64", "-nz", "64", "-t", "1", "-d"],
+    ["slab", "-nx", "64", "-ny", "32", "-nz", "128", "-t", "3", "-s", "Z_Then_YX", "-i", "2"],
+    ["slab", "-nx", "64", "-ny", "64", "-nz", "64", "-t", "4", "-d", "-comm", "All2All"],
+    ["pencil", "-nx", "32", "-ny", "64", "-nz", "64", "-p1", "1", "-p2", "1", "-t", "1", "-f", "2", "-d"],
+    ["pencil", "-nx", "64", "-ny", "64", "-nz", "64", "-p1", "1", "-p2", "1", "-t", "4", "-d"],
+    ["slab", "-nx", "64", "-ny", "64", "-nz", "64", "-t", "0", "-i", "2", "-w", "1"],
+    ["slab", "-nx", "64", "-ny", "64", "-nz", "64", "-t", "2", "-d"],
+])
+def test_cli_testcases(argv):
+    """The reference's CLI testcases 0-4 (tests/src/slab/main.cpp, tests/src/pencil/main.cpp) on one rank."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "cli.py"), *argv], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Result" in r.stdout or "Run complete" in r.stdout
