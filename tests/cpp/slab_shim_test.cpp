@@ -1,0 +1,91 @@
+// slab_shim_test.cpp — reference-shaped C++ caller on top of include/dfft.hpp (single rank).
+// Mirrors what /root/reference/tests/src/slab/random_dist_default.cu does with MPIcuFFT_Slab<T>:
+//   testcase 3 (forward -> inverse round trip, :528-623) and testcase 4 (spectral Laplacian of
+//   sin*sin*sin against -3 sqrt(N) f, :625-758), with tolerances and an exit code.
+// Build (tests/test_gpu_plan.py does it): g++ -std=c++17 -Iinclude -I/usr/local/cuda/include slab_shim_test.cpp
+//        -Ldistributedfft_b200 -ldfft -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,<repo>/distributedfft_b200
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#include "dfft.hpp"
+
+#define CUDA_CALL(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { std::printf("Error %d at %s:%d\n", int(e_), __FILE__, __LINE__); return 2; } } while (0)
+
+template <typename Plan>
+static int run(const char* name, Plan& fft, size_t Nx, size_t Ny, size_t Nz) {
+    GlobalSize gs(Nx, Ny, Nz);
+    fft.initFFT(&gs, nullptr, true);
+    size_t isz[3], osz[3], ost[3];
+    fft.getInSize(isz); fft.getOutSize(osz); fft.getOutStart(ost);
+    const size_t nin = isz[0] * isz[1] * isz[2], nout = osz[0] * osz[1] * osz[2];
+    const double N = double(Nx) * Ny * Nz, pi = 3.14159265358979323846;
+    std::vector<double> f(nin), back(nin);
+    for (size_t x = 0; x < isz[0]; ++x)
+        for (size_t y = 0; y < isz[1]; ++y)
+            for (size_t z = 0; z < isz[2]; ++z)
+                f[(x * isz[1] + y) * isz[2] + z] = std::sin(2 * pi * x / Nx) * std::sin(2 * pi * y / Ny) * std::sin(2 * pi * z / Nz);
+    double *in_d, *back_d;
+    void* out_d;
+    CUDA_CALL(cudaMalloc(&in_d, nin * sizeof(double)));
+    CUDA_CALL(cudaMalloc(&back_d, nin * sizeof(double)));
+    CUDA_CALL(cudaMalloc(&out_d, fft.getDomainSize()));
+    CUDA_CALL(cudaMemcpy(in_d, f.data(), nin * sizeof(double), cudaMemcpyHostToDevice));
+    // testcase 3: round trip
+    fft.execR2C(out_d, in_d);
+    fft.execC2R(back_d, out_d);
+    CUDA_CALL(cudaMemcpy(back.data(), back_d, nin * sizeof(double), cudaMemcpyDeviceToHost));
+    double e3 = 0;
+    for (size_t i = 0; i < nin; ++i) e3 = std::fmax(e3, std::fabs(back[i] / N - f[i]));
+    // testcase 4: multiply the spectrum by -(k1^2+k2^2+k3^2)/sqrt(N) on the host, inverse, compare
+    std::vector<double> spec(2 * nout);
+    fft.execR2C(out_d, in_d);
+    CUDA_CALL(cudaMemcpy(spec.data(), out_d, 2 * nout * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t x = 0; x < osz[0]; ++x)
+        for (size_t y = 0; y < osz[1]; ++y)
+            for (size_t z = 0; z < osz[2]; ++z) {
+                const double gx = double(x + ost[0]), gy = double(y + ost[1]), gz = double(z + ost[2]);
+                const double k1 = gx <= Nx / 2 ? gx : gx - double(Nx), k2 = gy <= Ny / 2 ? gy : gy - double(Ny), k3 = gz;
+                const double c = -(k1 * k1 + k2 * k2 + k3 * k3) / std::sqrt(N);
+                const size_t i = (x * osz[1] + y) * osz[2] + z;
+                spec[2 * i] *= c; spec[2 * i + 1] *= c;
+            }
+    CUDA_CALL(cudaMemcpy(out_d, spec.data(), 2 * nout * sizeof(double), cudaMemcpyHostToDevice));
+    fft.execC2R(back_d, out_d);
+    CUDA_CALL(cudaMemcpy(back.data(), back_d, nin * sizeof(double), cudaMemcpyDeviceToHost));
+    double e4 = 0;
+    const double amp = 3.0 * std::sqrt(N);
+    for (size_t i = 0; i < nin; ++i) e4 = std::fmax(e4, std::fabs(back[i] - (-amp * f[i])));
+    std::printf("%s %zux%zux%zu  Result (roundtrip max): %.3e   Result (laplacian max / 3sqrt(N)): %.3e\n", name, Nx, Ny, Nz, e3, e4 / amp);
+    cudaFree(in_d); cudaFree(back_d); cudaFree(out_d);
+    return (e3 < 1e-12 && e4 / amp < 1e-12) ? 0 : 1;
+}
+
+int main() {
+    dfft_comm_t comm;
+    DFFT_CALL(dfft_comm_create(0, 1, nullptr, 0, &comm));
+    Configurations config{true, 0, Peer2Peer, Sync, "", Peer2Peer, Sync};
+    int rc = 0;
+    {
+        MPIcuFFT_Slab<double> fft(config, comm);
+        rc |= run("MPIcuFFT_Slab<double>", fft, 64, 32, 128);
+    }
+    {
+        MPIcuFFT_Slab_Z_Then_YX<double> fft(config, comm);
+        rc |= run("MPIcuFFT_Slab_Z_Then_YX<double>", fft, 32, 64, 64);
+    }
+    {
+        MPIcuFFT_Pencil<double> fft(config, comm);
+        Pencil_Partition part(1, 1);
+        GlobalSize gs(16, 16, 32);
+        fft.initFFT(&gs, &part, true);
+        Partition_Dimensions a, b, c;
+        fft.getPartitionDimensions(a, b, c);
+        if (a.size_x[0] != 16 || b.size_z[0] != 17 || c.size_y[0] != 16) { std::printf("getPartitionDimensions wrong\n"); rc |= 1; }
+    }
+    dfft_comm_destroy(comm);
+    std::printf(rc ? "FAILED\n" : "PASSED\n");
+    return rc;
+}

@@ -199,3 +199,16 @@ def test_cli_testcases(argv):
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "cli.py"), *argv], capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "Result" in r.stdout or "Run complete" in r.stdout
+
+
+def test_cpp_shim_caller(tmp_path):
+    """Reference-shaped C++ caller over include/dfft.hpp (MPIcuFFT_Slab<double> etc.): round trip + Laplacian."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "slab_shim_test")
+    libdir = os.path.join(root, "distributedfft_b200")
+    subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(root, "include"), "-I/usr/local/cuda/include",
+                    os.path.join(root, "tests", "cpp", "slab_shim_test.cpp"), "-o", exe, "-L" + libdir, "-ldfft",
+                    "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
