@@ -79,10 +79,14 @@ static cudaError_t make_table(size_t count, size_t denom, void** dev) {
 
 struct Tables {
     int prec = DFFT_F64;
+    bool dry = false;  // geometry-only plans: no device allocations, segment tables live on the host
+    std::map<const void*, std::vector<unsigned char>> host_tabs;  // segment table pointer -> host copy
+    std::vector<std::vector<unsigned char>*> dry_store;
     std::map<int, void*> tw;   // log2n -> exp(-2 pi i m / n), m < n
     std::map<int, void*> tw2;  // log2m -> exp(-2 pi i k / 2m), k <= m/2
     std::vector<void*> bytes;  // seg_of_n tables
     cudaError_t get_tw(int log2n, void** out) {
+        if (dry) { *out = nullptr; return cudaSuccess; }
         auto it = tw.find(log2n);
         if (it == tw.end()) {
             void* d = nullptr;
@@ -95,6 +99,7 @@ struct Tables {
         return cudaSuccess;
     }
     cudaError_t get_tw2(int log2m, void** out) {
+        if (dry) { *out = nullptr; return cudaSuccess; }
         auto it = tw2.find(log2m);
         if (it == tw2.end()) {
             void* d = nullptr;
@@ -111,11 +116,19 @@ struct Tables {
         std::vector<unsigned char> h(n);
         for (size_t p = 0; p < s.size.size(); ++p)
             for (size_t k = 0; k < s.size[p]; ++k) h[s.start[p] + k] = (unsigned char)p;
+        if (dry) {
+            auto* keep = new std::vector<unsigned char>(h);
+            dry_store.push_back(keep);
+            host_tabs[keep->data()] = h;
+            *out = keep->data();
+            return cudaSuccess;
+        }
         void* d = nullptr;
         cudaError_t e = cudaMalloc(&d, n ? n : 1);
         if (e != cudaSuccess) return e;
         e = cudaMemcpy(d, h.data(), n, cudaMemcpyHostToDevice);
         bytes.push_back(d);
+        host_tabs[d] = h;
         *out = (const unsigned char*)d;
         return e;
     }
@@ -123,7 +136,8 @@ struct Tables {
         for (auto& kv : tw) cudaFree(kv.second);
         for (auto& kv : tw2) cudaFree(kv.second);
         for (void* p : bytes) cudaFree(p);
-        tw.clear(); tw2.clear(); bytes.clear();
+        for (auto* v : dry_store) delete v;
+        tw.clear(); tw2.clear(); bytes.clear(); dry_store.clear(); host_tabs.clear();
     }
 };
 
@@ -162,6 +176,7 @@ using namespace dfft;
 struct dfft_comm_s {
     int rank = 0, nranks = 1, device = 0;
     ncclComm_t nccl = nullptr;
+    bool dry = false;  // geometry-only: plans never touch CUDA (dfft_comm_create_dry)
 };
 
 namespace dfft {
@@ -229,6 +244,7 @@ struct dfft_plan_s {
     std::vector<cudaEvent_t> sync_events;
     cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
     int xchg_ctas = 0;                            // SMs given to the exchange pass in overlapped schedules
+    int blocked_ch = 0;                           // > 0: slab forward keeps the y->x intermediate as [b/CH][Nx][CH]
     cudaStream_t own_stream = nullptr, last_stream = nullptr;  // last_stream: stream of the last exec
     Tables tabs;
     // schedules: [fwd/inv][d-1]
@@ -499,7 +515,18 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
         // transposition 2: scatter along y over G2 (column of the grid, or all ranks for the slab)
         Step x2;
         const bool t2_a2a = !dir2;
-        if (dir2) {
+        const size_t CH = (dir2 && g.decomp == DFFT_SLAB_ZY_THEN_X && !(t1_a2a)) ? size_t(p->blocked_ch) : 0;
+        if (dir2 && CH) {
+            // blocked hand-over: receiver q holds [(ny_q*nzc)/CH][nx][CH]
+            s2.prm.A1 = int(nz_j / CH); s2.prm.B = int(CH);
+            s2.prm.in.seg[0].sA1 = (long long)CH;
+            s2.prm.tile_pref = 1;
+            seg_view(s2.prm.out, tab_y_out, G2, [&](int, int r) {
+                SegN sn = mkseg(eptr(slotp(D2, r), x0_i * CH, es), (long long)CH, (long long)(g.nx * CH), (long long)(nz_j * g.nx), 0);
+                return sn;
+            });
+            for (size_t q = 0; q < G2.size(); ++q) s2.prm.out.seg[q].n0 = int(g.oy.start[q]);
+        } else if (dir2) {
             seg_view(s2.prm.out, tab_y_out, G2, [&](int q, int r) {
                 const size_t nyq = g.oy.size[q];
                 return mkseg(eptr(slotp(D2, r), x0_i * nyq * nz_j, es), (long long)(nyq * nz_j), 0, (long long)nz_j, g.oy.start[q]);
@@ -521,9 +548,15 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
         rc = new_pass(PASS_C2C_TILED, g.nx, "1D FFT X-Direction", s3);
         if (rc) return rc;
         s3.label = "x pass";
-        s3.prm.A0 = 1; s3.prm.A1 = 1; s3.prm.B = int(oy_i * nz_j);
-        s3.prm.in = single_view(t2_a2a ? slotp(SR, me) : slotp(D2, me), 0, 0, (long long)(oy_i * nz_j));
-        s3.prm.out = single_view(nullptr, 0, 0, (long long)(oy_i * nz_j));
+        if (CH) {
+            s3.prm.A0 = 1; s3.prm.A1 = int(oy_i * nz_j / CH); s3.prm.B = int(CH);
+            s3.prm.in = single_view(slotp(D2, me), 0, (long long)(g.nx * CH), (long long)CH);
+            s3.prm.out = single_view(nullptr, 0, (long long)CH, (long long)(oy_i * nz_j));
+        } else {
+            s3.prm.A0 = 1; s3.prm.A1 = 1; s3.prm.B = int(oy_i * nz_j);
+            s3.prm.in = single_view(t2_a2a ? slotp(SR, me) : slotp(D2, me), 0, 0, (long long)(oy_i * nz_j));
+            s3.prm.out = single_view(nullptr, 0, 0, (long long)(oy_i * nz_j));
+        }
         s3.out_user = 2;
         sc.steps.push_back(s3);
         sc.built = true;
@@ -746,7 +779,16 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
     const size_t NG = std::min<size_t>(4, nx_p);
     const size_t NS = nzc >= 128 ? 4 : (nzc >= 32 ? 2 : 1);
     groups.make(nx_p, NG);
-    chunks.make(nzc, NS);
+    const size_t CH = inverse ? 0 : size_t(p->blocked_ch);
+    if (CH) {  // z chunks are whole multiples of the block width
+        Split u;
+        u.make(nzc / CH, std::min<size_t>(NS, nzc / CH));
+        chunks.size.clear(); chunks.start.clear();
+        for (size_t c = 0; c < u.size.size(); ++c) { chunks.size.push_back(u.size[c] * CH); chunks.start.push_back(u.start[c] * CH); }
+    } else {
+        chunks.make(nzc, NS);
+    }
+    const size_t NSc = chunks.size.size();
     const unsigned char *tab_y = nullptr, *tab_x = nullptr;
     if (T.seg_table(g.oy, &tab_y) != cudaSuccess || T.seg_table(g.sx, &tab_x) != cudaSuccess) return fail(DFFT_ERR_CUDA, "segment table");
 
@@ -758,7 +800,7 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
     int rc;
 
     if (!inverse) {
-        std::vector<int> ev_z(NG), ev_y(NS);
+        std::vector<int> ev_z(NG), ev_y(NSc);
         for (size_t gi = 0; gi < NG; ++gi) {
             Step s;
             rc = new_pass(c2c ? PASS_C2C_CONTIG : PASS_R2C, c2c ? g.nz : g.nz / 2, c2c ? "z pass" : "z pass (R2C)", s);
@@ -773,19 +815,29 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
             s.record = ev_z[gi] = nev++;
             sc.steps.push_back(s);
         }
-        for (size_t c = 0; c < NS; ++c) {
+        for (size_t c = 0; c < NSc; ++c) {
             const size_t z0 = chunks.start[c], zc = chunks.size[c];
             for (size_t gi = 0; gi < NG; ++gi) {
                 Step s;
                 rc = new_pass(PASS_C2C_TILED, ny, "y pass", s);
                 if (rc) return rc;
                 const size_t pl0 = groups.start[gi], npl = groups.size[gi];
+                if (CH) {
+                    s.prm.A0 = int(npl); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
+                    s.prm.in = single_view(eptr(slotp(D1, me), pl0 * ny * nzc + z0, es), (long long)(ny * nzc), (long long)CH, (long long)nzc);
+                    s.prm.tile_pref = 1;
+                    seg_view(s.prm.out, tab_y, G2, [&](int, int r) {
+                        return mkseg(eptr(slotp(D2, r), (x0 + pl0) * CH + (z0 / CH) * nx * CH, es), (long long)CH, (long long)(nx * CH), (long long)(nzc * nx), 0);
+                    });
+                    for (size_t q = 0; q < G2.size(); ++q) s.prm.out.seg[q].n0 = int(g.oy.start[q]);
+                } else {
                 s.prm.A0 = int(npl); s.prm.A1 = 1; s.prm.B = int(zc);
                 s.prm.in = single_view(eptr(slotp(D1, me), pl0 * ny * nzc + z0, es), (long long)(ny * nzc), 0, (long long)nzc);
                 seg_view(s.prm.out, tab_y, G2, [&](int q, int r) {
                     const size_t nyq = g.oy.size[q];
                     return mkseg(eptr(slotp(D2, r), (x0 + pl0) * nyq * nzc + z0, es), (long long)(nyq * nzc), 0, (long long)nzc, g.oy.start[q]);
                 });
+                }
                 s.prm.max_ctas = p->xchg_ctas;
                 s.stream = 1;
                 if (c == 0) s.waits.push_back(ev_z[gi]);
@@ -794,7 +846,7 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
                 sc.steps.push_back(s);
             }
         }
-        for (size_t c = 0; c < NS; ++c) {
+        for (size_t c = 0; c < NSc; ++c) {
             const size_t z0 = chunks.start[c], zc = chunks.size[c];
             Step r = rendezvous(2, 2, 2);
             r.waits.push_back(ev_y[c]);
@@ -802,9 +854,16 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
             Step s;
             rc = new_pass(PASS_C2C_TILED, nx, "x pass", s);
             if (rc) return rc;
+            if (CH) {
+                // in: [(y_loc*(nzc/CH) + zc)][nx][CH]; a0 = y_loc, a1 = zc within this chunk
+                s.prm.A0 = int(oy_me); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
+                s.prm.in = single_view(eptr(slotp(D2, me), (z0 / CH) * nx * CH, es), (long long)((nzc / CH) * nx * CH), (long long)(nx * CH), (long long)CH);
+                s.prm.out = single_view((void*)(size_t)(z0 * es), (long long)nzc, (long long)CH, (long long)(oy_me * nzc));
+            } else {
             s.prm.A0 = 1; s.prm.A1 = int(oy_me); s.prm.B = int(zc);
             s.prm.in = single_view(eptr(slotp(D2, me), z0, es), 0, (long long)nzc, (long long)(oy_me * nzc));
             s.prm.out = single_view((void*)(size_t)(z0 * es), 0, (long long)nzc, (long long)(oy_me * nzc));
+            }
             s.out_user = 2;
             s.stream = 2;
             sc.steps.push_back(s);
@@ -1071,6 +1130,7 @@ static int exec_common(dfft_plan_t p, void* out, const void* in, int inverse, in
     // sync == true: the plain calls run on the plan's own stream; _async calls use exactly the stream given
     // (NULL = the CUDA default stream)
     if (!p) return fail(DFFT_ERR_INVALID, "null plan");
+    if (p->comm->dry) return fail(DFFT_ERR_STATE, "geometry-only plan (dfft_comm_create_dry) cannot execute");
     if (!p->work) return fail(DFFT_ERR_STATE, "plan has no work area (call dfft_set_work_area)");
     if (p->g.transform != need_transform) return fail(DFFT_ERR_INVALID, need_transform == DFFT_C2C ? "plan was created for R2C/C2R" : "plan was created for C2C");
     if (d < 1 || d > 3) return fail(DFFT_ERR_INVALID, "d must be 1, 2 or 3");
@@ -1202,6 +1262,14 @@ int dfft_comm_create(int rank, int nranks, const void* id, int device, dfft_comm
     *comm = c;
     return DFFT_SUCCESS;
 }
+int dfft_comm_create_dry(int rank, int nranks, dfft_comm_t* comm) {
+    if (!comm || nranks < 1 || rank < 0 || rank >= nranks) return fail(DFFT_ERR_INVALID, "bad rank / nranks");
+    if (nranks > MAXSEG) return fail(DFFT_ERR_UNSUPPORTED, "at most " + std::to_string(MAXSEG) + " ranks");
+    dfft_comm_s* c = new dfft_comm_s();
+    c->rank = rank; c->nranks = nranks; c->device = -1; c->dry = true;
+    *comm = c;
+    return DFFT_SUCCESS;
+}
 int dfft_comm_destroy(dfft_comm_t c) {
     if (!c) return DFFT_SUCCESS;
     if (c->nccl) ncclCommDestroy(c->nccl);
@@ -1234,7 +1302,8 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
     if (!comm || !plan) return fail(DFFT_ERR_INVALID, "null comm / plan");
     if (precision != DFFT_F32 && precision != DFFT_F64) return fail(DFFT_ERR_INVALID, "bad precision");
     if (transform != DFFT_R2C && transform != DFFT_C2C) return fail(DFFT_ERR_INVALID, "bad transform");
-    CK_CUDA(cudaSetDevice(comm->device));
+    const bool dry = comm->dry;
+    if (!dry) CK_CUDA(cudaSetDevice(comm->device));
     const auto t_init0 = std::chrono::steady_clock::now();
     dfft_plan_s* p = new dfft_plan_s();
     p->comm = comm;
@@ -1249,6 +1318,7 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
     p->prec = precision;
     p->esize = precision == DFFT_F64 ? 16 : 8;
     p->tabs.prec = precision;
+    p->tabs.dry = dry;
     if (!p->g.init(decomp, transform, nx, ny, nz, p1, p2, p->P)) {
         delete p;
         return fail(DFFT_ERR_INVALID, "invalid partition: P1*P2 must equal the communicator size");
@@ -1292,6 +1362,25 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
     p->domain_bytes = g.domain_elems(me) * p->esize;
     p->slot_bytes = ((dom * p->esize + 255) / 256) * 256;
     p->work_bytes = p->slot_bytes * p->nslots;
+    {
+        const char* e = getenv("DFFT_XCHG_CTAS");
+        p->xchg_ctas = e ? atoi(e) : 128;
+        // Blocked intermediate layout for the slab's y -> x hand-over: [b/CH][Nx][CH] makes every x-pass tile a
+        // compact block instead of Nx rows in Nx different 2 MB pages (x pass +14..16 %, y pass -3 %,
+        // tools/layout_probe.py).  Needs CH | Nzc, i.e. complex plans with power-of-two Nz.  DFFT_BLOCKED=0 disables.
+        const char* eb = getenv("DFFT_BLOCKED");
+        const int ch = eb ? atoi(eb) : 16;
+        p->blocked_ch = (decomp == DFFT_SLAB_ZY_THEN_X && ch > 0 && g.nzc % size_t(ch) == 0 && g.nzc >= size_t(4 * ch)) ? ch : 0;
+    }
+    if (dry) {
+        // fake, rank-distinct slot addresses: ((rank + 1) << 44) + slot * slot_bytes; user buffers are offsets
+        p->slot_ptr.assign(p->nslots, std::vector<void*>(P, nullptr));
+        for (int s_ = 0; s_ < p->nslots; ++s_)
+            for (int r = 0; r < P; ++r) p->slot_ptr[s_][r] = (void*)(((unsigned long long)(r + 1) << 44) + (unsigned long long)s_ * p->slot_bytes);
+        p->work = p->slot_ptr[0][me];
+        *plan = p;
+        return DFFT_SUCCESS;
+    }
     cudaError_t ce = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { delete p; return fail(DFFT_ERR_CUDA, "cudaStreamCreate failed"); }
     {
@@ -1305,8 +1394,6 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
             delete p;
             return fail(DFFT_ERR_CUDA, "stream / event creation failed");
         }
-        const char* e = getenv("DFFT_XCHG_CTAS");
-        p->xchg_ctas = e ? atoi(e) : 128;
     }
     int rc = plan_setup_flags(p);
     if (rc == DFFT_SUCCESS && allocate) rc = plan_setup_memory(p, nullptr);
@@ -1337,6 +1424,12 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
 
 int dfft_plan_destroy(dfft_plan_t p) {
     if (!p) return DFFT_SUCCESS;
+    if (p->comm->dry) {
+        p->work = nullptr;
+        p->tabs.release();
+        delete p;
+        return DFFT_SUCCESS;
+    }
     cudaSetDevice(p->comm->device);
     cudaDeviceSynchronize();
     plan_release_memory(p);
@@ -1497,6 +1590,74 @@ int dfft_get_step_times(dfft_plan_t p, double* ms, int capacity) {
         ms[n] = f;
     }
     return n;
+}
+// JSON description of a schedule (test hook: tests/test_schedule_emulation.py replays it with numpy)
+static void json_view(std::string& o, const View& v, const Tables& T) {
+    o += "{\"nseg\":" + std::to_string(v.nseg) + ",\"sN\":" + std::to_string(v.sN) + ",\"segs\":[";
+    for (int i = 0; i < v.nseg; ++i) {
+        const Seg& g = v.seg[i];
+        if (i) o += ",";
+        o += "{\"base\":" + std::to_string((unsigned long long)g.base) + ",\"sA0\":" + std::to_string(g.sA0) + ",\"sA1\":" + std::to_string(g.sA1) +
+             ",\"n0\":" + std::to_string(g.n0) + "}";
+    }
+    o += "],\"seg_of_n\":[";
+    if (v.nseg > 1) {
+        auto it = T.host_tabs.find(v.seg_of_n);
+        if (it != T.host_tabs.end())
+            for (size_t i = 0; i < it->second.size(); ++i) { if (i) o += ","; o += std::to_string(int(it->second[i])); }
+    }
+    o += "]}";
+}
+int dfft_plan_describe(dfft_plan_t p, int inverse, int d, char* buf, size_t capacity, size_t* needed) {
+    if (!p || d < 1 || d > 3) return fail(DFFT_ERR_INVALID, "bad arguments");
+    Schedule& sc = p->sched[inverse ? 1 : 0][d - 1];
+    if (!sc.built) {
+        g_view_error = false;
+        const bool want_overlap = p->cfg.send_method == DFFT_SEND_STREAMS && d == 3 && p->P > 1 && p->g.decomp == DFFT_SLAB_ZY_THEN_X && p->direct2;
+        int rc = want_overlap ? build_overlapped_slab(p, inverse ? 1 : 0, sc) : build_schedule(p, inverse ? 1 : 0, d, sc);
+        if (rc) return rc;
+        if (g_view_error) return fail(DFFT_ERR_STATE, "internal: segments of one view disagree on the axis stride");
+    }
+    std::string o = "{\"rank\":" + std::to_string(p->rank) + ",\"esize\":" + std::to_string(p->esize) + ",\"slot_bytes\":" + std::to_string(p->slot_bytes) +
+                    ",\"nslots\":" + std::to_string(p->nslots) + ",\"overlapped\":" + (sc.overlapped ? "true" : "false") + ",\"slots\":[";
+    for (int s_ = 0; s_ < p->nslots; ++s_) {
+        if (s_) o += ",";
+        o += "[";
+        for (int r = 0; r < p->P; ++r) { if (r) o += ","; o += std::to_string((unsigned long long)p->slot_ptr[s_][r]); }
+        o += "]";
+    }
+    o += "],\"steps\":[";
+    bool first = true;
+    for (const Step& s_ : sc.steps) {
+        if (!first) o += ",";
+        first = false;
+        o += "{\"type\":" + std::to_string(int(s_.type)) + ",\"label\":\"" + s_.label + "\",\"stream\":" + std::to_string(s_.stream);
+        if (s_.type == STEP_PASS) {
+            o += ",\"kind\":" + std::to_string(int(s_.kind)) + ",\"log2n\":" + std::to_string(s_.log2n) + ",\"A0\":" + std::to_string(s_.prm.A0) +
+                 ",\"A1\":" + std::to_string(s_.prm.A1) + ",\"B\":" + std::to_string(s_.prm.B) + ",\"inverse\":" + std::to_string(s_.prm.inverse) +
+                 ",\"in_user\":" + std::to_string(s_.in_user) + ",\"out_user\":" + std::to_string(s_.out_user) + ",\"in\":";
+            json_view(o, s_.prm.in, p->tabs);
+            o += ",\"out\":";
+            json_view(o, s_.prm.out, p->tabs);
+        } else if (s_.type == STEP_RENDEZVOUS) {
+            o += ",\"group\":" + std::to_string(s_.group);
+        } else {
+            o += ",\"group\":" + std::to_string(s_.group) + ",\"send_slot\":" + std::to_string(s_.send_slot) + ",\"recv_slot\":" + std::to_string(s_.recv_slot) + ",\"peers\":[";
+            const std::vector<int>& G = p->grp[s_.group];
+            for (size_t q = 0; q < G.size(); ++q) {
+                if (q) o += ",";
+                o += "{\"rank\":" + std::to_string(G[q]) + ",\"scount\":" + std::to_string(s_.scount[q]) + ",\"soff\":" + std::to_string(s_.soff[q]) +
+                     ",\"rcount\":" + std::to_string(s_.rcount[q]) + ",\"roff\":" + std::to_string(s_.roff[q]) + "}";
+            }
+            o += "]";
+        }
+        o += "}";
+    }
+    o += "]}";
+    if (needed) *needed = o.size() + 1;
+    if (buf && capacity > o.size()) memcpy(buf, o.c_str(), o.size() + 1);
+    else if (buf && capacity) buf[0] = 0;
+    return DFFT_SUCCESS;
 }
 int dfft_timer_gather(dfft_plan_t p) {
     if (!p) return fail(DFFT_ERR_INVALID, "null plan");

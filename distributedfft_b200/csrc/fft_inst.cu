@@ -29,19 +29,13 @@ static int persistent_ctas(K kernel, int threads, size_t smem) {
 // DFFT_PIPE=1 selects the persistent register-prefetch kernels where the tile shape allows 255 registers
 // per thread (measured slower than two resident CTAs per SM on B200 for most shapes, so off by default).
 static int pipe_mode() {
-    static int mode = [] {
-        const char* e = getenv("DFFT_PIPE");
-        return e ? atoi(e) : 0;
-    }();
-    return mode;
+    const char* e = getenv("DFFT_PIPE");  // read per launch (cheap) so that one process can compare variants
+    return e ? atoi(e) : 0;
 }
 
 static int wide_tiles() {
-    static int mode = [] {
-        const char* e = getenv("DFFT_WIDE_TILES");
-        return e ? atoi(e) : 0;
-    }();
-    return mode;
+    const char* e = getenv("DFFT_WIDE_TILES");
+    return e ? atoi(e) : 0;
 }
 
 template <typename T, int LOG2N, int TB>
@@ -117,7 +111,8 @@ cudaError_t launch_pass(PassKind kind, const FftParams& p, cudaStream_t stream) 
                 const int w = wide_tiles();
                 const bool far_rows = (unsigned long long)p.in.sN * sizeof(cx<T>) >= (1ull << 20) ||
                                       (unsigned long long)p.out.sN * sizeof(cx<T>) >= (1ull << 20);
-                if (w > 0 || (w == 0 && LOG2N >= 10 && far_rows)) return launch_tiled<T, LOG2N, S::TBT_WIDE>(p, stream, lines);
+                const bool wide = w > 0 || p.tile_pref == 2 || (w == 0 && p.tile_pref == 0 && LOG2N >= 10 && far_rows);
+                if (wide && w >= 0 && p.tile_pref != 1) return launch_tiled<T, LOG2N, S::TBT_WIDE>(p, stream, lines);
             }
             return launch_tiled<T, LOG2N, S::TBT>(p, stream, lines);
         }

@@ -55,7 +55,7 @@ struct FftParams {
     const void* tw2;  // R2C/C2R only: exp(-2*pi*i*k/(2N)), k <= N/2
     int max_ctas;     // > 0: run as a persistent kernel on at most this many CTAs (SM partitioning for the
                       // overlapped schedule: the exchange pass keeps a few SMs, the local passes the rest)
-    int pad_;
+    int tile_pref;    // TILED: 0 automatic, 1 narrow tiles, 2 wide tiles
 };
 
 enum PassKind { PASS_C2C_CONTIG = 0, PASS_C2C_TILED = 1, PASS_R2C = 2, PASS_C2R = 3 };

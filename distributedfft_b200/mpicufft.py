@@ -88,10 +88,18 @@ class MPIcuFFT:
                  precision: str = "double", transform: str = "r2c"):
         self.config = config
         self.comm = comm if comm is not None else Comm()
-        self.precision = F64 if precision in ("double", "f64", F64) and precision != F32 else F32
-        if precision in ("float", "f32"):
+        if precision in ("double", "f64", "float64"):
+            self.precision = F64
+        elif precision in ("float", "f32", "float32"):
             self.precision = F32
-        self.transform = C2C if transform in ("c2c", C2C) and transform != R2C else R2C
+        else:
+            raise ValueError(f"precision must be 'double' or 'float', got {precision!r}")
+        if transform in ("r2c", "R2C"):
+            self.transform = R2C
+        elif transform in ("c2c", "C2C"):
+            self.transform = C2C
+        else:
+            raise ValueError(f"transform must be 'r2c' or 'c2c', got {transform!r}")
         self._h = None
         self.initialized = False
 

@@ -185,6 +185,14 @@ int dfft_fft1d_contig(int precision, int kind, int direction, size_t n, size_t l
 int dfft_fft1d_strided(int precision, int direction, size_t a, size_t n, size_t b, void* out, const void* in,
                        void* stream);
 
+/* ---- test hooks -----------------------------------------------------------------------------------------
+ * Geometry-only communicator: plans created on it never touch CUDA or NCCL (slot addresses are synthetic,
+ * ((rank+1) << 44) + slot * slot_bytes) and cannot execute; dfft_plan_describe returns the step list of a
+ * schedule (passes with their views, rendezvous, all-to-all counts) as JSON so that the CPU tests can replay
+ * the data movement of any rank count with numpy (tests/test_schedule_emulation.py). */
+int dfft_comm_create_dry(int rank, int nranks, dfft_comm_t* comm);
+int dfft_plan_describe(dfft_plan_t plan, int inverse, int d, char* buf, size_t capacity, size_t* needed);
+
 /* Batched 1D C2C along n of element (i0, i1, n, ib) at  i0*strides[0] + i1*strides[1] + n*strides[2] + ib
  * (elements; ib contiguous, extents a0 x a1 x n x b) — the general strided view the plan's passes use. */
 int dfft_fft1d_general(int precision, int direction, size_t n, size_t a0, size_t a1, size_t b, void* out,

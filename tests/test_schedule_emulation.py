@@ -1,0 +1,248 @@
+"""Replays the library's schedules on the CPU for any rank count.
+
+dfft_comm_create_dry gives a geometry-only communicator; dfft_plan_describe returns, per rank, the exact step
+list the GPU executes — every FFT pass with its segmented input / output views (base addresses, strides,
+segment tables), rendezvous points and all-to-all counts.  This test builds the plans of all P ranks, lays
+the synthetic slot addresses out in numpy arrays, executes the steps in lock step (numpy FFTs for the passes,
+the views for all data movement) and compares every rank's output block with the oracle's block of the global
+transform.  It covers what cannot be run here on a GPU: 4- and 8-rank slab / z_then_yx / pencil grids, both
+exchange methods, forward and inverse, partial transforms, the overlapped (Streams) schedule and the blocked
+intermediate layout."""
+import ctypes as C
+import json
+
+import numpy as np
+import pytest
+
+import distributedfft_b200 as dfft
+from distributedfft_b200 import _lib
+from distributedfft_b200._lib import check, lib
+from oracle import dft_oracle as O
+
+USER_IN, USER_OUT = 1 << 60, 1 << 61  # synthetic address ranges of the caller's buffers
+
+
+def describe(rank, P, decomp, transform, shape, p1, p2, comm_method, send_method, inverse, d):
+    comm = C.c_void_p()
+    check(lib().dfft_comm_create_dry(rank, P, C.byref(comm)))
+    cfg = _lib.dfft_config(1, 0, comm_method, send_method, None, comm_method, send_method)
+    plan = C.c_void_p()
+    check(lib().dfft_plan_create(comm, C.byref(cfg), decomp, dfft.F64, transform, shape[0], shape[1], shape[2], p1, p2, 1, C.byref(plan)))
+    need = C.c_size_t()
+    check(lib().dfft_plan_describe(plan, inverse, d, None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    check(lib().dfft_plan_describe(plan, inverse, d, buf, need.value, C.byref(need)))
+    sched = json.loads(buf.value.decode())
+    lib().dfft_plan_destroy(plan)
+    lib().dfft_comm_destroy(comm)
+    return sched
+
+
+class Memory:
+    """complex128 arrays keyed by synthetic base address"""
+
+    def __init__(self):
+        self.regions = []  # (base_bytes, array)
+
+    def add(self, base, nelem):
+        arr = np.zeros(nelem, dtype=np.complex128)
+        self.regions.append((base, arr))
+        return arr
+
+    def resolve(self, addr):
+        for base, arr in self.regions:
+            if base <= addr < base + arr.size * 16:
+                assert (addr - base) % 16 == 0
+                return arr, (addr - base) // 16
+        raise KeyError(hex(addr))
+
+
+def view_indices(view, A0, A1, N, B, user_base=None):
+    """flat (array, index) for every element (a0, a1, n, b) of a view, as index arrays per segment"""
+    out = []
+    seg_of_n = np.array(view["seg_of_n"], dtype=np.int64) if view["nseg"] > 1 else np.zeros(N, dtype=np.int64)
+    a0 = np.arange(A0)[:, None, None, None]
+    a1 = np.arange(A1)[None, :, None, None]
+    b = np.arange(B)[None, None, None, :]
+    for s, seg in enumerate(view["segs"]):
+        ns = np.nonzero(seg_of_n[:N] == s)[0]
+        if ns.size == 0:
+            continue
+        n = ns[None, None, :, None]
+        off = a0 * seg["sA0"] + a1 * seg["sA1"] + (n - seg["n0"]) * view["sN"] + b
+        base = seg["base"] if user_base is None else user_base + seg["base"]
+        out.append((base, ns, off))
+    return out
+
+
+def run_case(P, decomp, transform, shape, p1, p2, comm_method, send_method, inverse, d):
+    nx, ny, nz = shape
+    c2c = transform == dfft.C2C
+    scheds = [describe(r, P, decomp, transform, shape, p1, p2, comm_method, send_method, inverse, d) for r in range(P)]
+    mems = []
+    lay = lambda r, w: dfft.layout(decomp, transform, nx, ny, nz, p1, p2, r, w)
+    # global data and per-rank user buffers (real buffers are stored as complex pairs, like the kernels read them)
+    if c2c:
+        xg = O.complex_input(shape)
+        spec = O.fft_c2c(xg, d)
+    else:
+        xg = O.real_input(shape)
+        spec = O.fft_r2c(xg, d)
+    mem = Memory()
+    for r in range(P):
+        sc = scheds[r]
+        for s_ in range(sc["nslots"]):
+            mem.add(sc["slots"][s_][r], sc["slot_bytes"] // 16)
+    uin, uout = [], []
+    for r in range(P):
+        isz, ist = lay(r, 0)
+        osz, ost = lay(r, d)
+        dom = max(int(np.prod(lay(r, w)[0][:2])) * (nz if c2c else nz // 2 + 1) for w in (1, 2, 3))
+        if not inverse:
+            blk = np.ascontiguousarray(O.block(xg, ist, isz))
+            src = blk.astype(np.complex128).ravel() if c2c else blk.ravel().view(np.complex128)
+            a = mem.add(USER_IN + (r << 48), max(src.size, 1)); a[:src.size] = src
+            uin.append(a)
+            uout.append(mem.add(USER_OUT + (r << 48), dom))
+        else:
+            blk = np.ascontiguousarray(O.block(spec, ost, osz)).ravel()
+            a = mem.add(USER_IN + (r << 48), dom); a[:blk.size] = blk
+            uin.append(a)
+            nreal = int(np.prod(isz))
+            uout.append(mem.add(USER_OUT + (r << 48), nreal if c2c else nreal // 2))
+    nsteps = len(scheds[0]["steps"])
+    assert all(len(s["steps"]) == nsteps for s in scheds)
+    # hazard bookkeeping: a slot written by another rank may only be read after a later rendezvous of the owner,
+    # and nobody may write into a peer's slot before its own entry rendezvous (previous exec finished everywhere)
+    slot_owner = {}
+    for r in range(P):
+        for s_ in range(scheds[r]["nslots"]):
+            slot_owner[scheds[r]["slots"][s_][r]] = (r, s_)
+    last_remote_write = {}
+    last_rdv = [-1] * P
+
+    def owner_of(addr):
+        for base, (q, s_) in slot_owner.items():
+            if base <= addr < base + scheds[q]["slot_bytes"]:
+                return q, s_
+        return None
+
+    for k in range(nsteps):
+        pending = []
+        for r in range(P):
+            st = scheds[r]["steps"][k]
+            if st["type"] == 1:
+                last_rdv[r] = k
+                continue
+            if st["type"] == 2:  # all-to-all-v between staging slots
+                sb = scheds[r]["slots"][st["send_slot"]][r]
+                for peer in st["peers"]:
+                    q = peer["rank"]
+                    rb = scheds[q]["slots"][st["recv_slot"]][q]
+                    mine = [pp for pp in scheds[q]["steps"][k]["peers"] if pp["rank"] == r][0]
+                    assert mine["rcount"] == peer["scount"]
+                    src, so = mem.resolve(sb + peer["soff"] * 16)
+                    dst, do = mem.resolve(rb + mine["roff"] * 16)
+                    pending.append((dst, do, src[so:so + peer["scount"]].copy()))
+                continue
+            N = 1 << st["log2n"]
+            A0, A1, B = st["A0"], st["A1"], st["B"]
+            kind = st["kind"]
+            if st["in_user"] != 1:
+                for seg in st["in"]["segs"]:
+                    own = owner_of(seg["base"])
+                    assert own is not None and own[0] == r, "passes only read local memory"
+                    w = last_remote_write.get(own, -1)
+                    assert w < 0 or w < last_rdv[r] <= k, f"rank {r} step {k} reads slot {own} written remotely at step {w} without a rendezvous"
+            if st["out_user"] != 2:
+                for seg in st["out"]["segs"]:
+                    own = owner_of(seg["base"])
+                    assert own is not None
+                    if own[0] != r:
+                        assert last_rdv[r] >= 0, f"rank {r} writes into rank {own[0]}'s slot before its entry rendezvous"
+                        last_remote_write[own] = k
+            ub_in = USER_IN + (r << 48) if st["in_user"] == 1 else None
+            ub_out = USER_OUT + (r << 48) if st["out_user"] == 2 else None
+            if kind in (0, 1):  # C2C
+                data = np.zeros((A0, A1, N, B), dtype=np.complex128)
+                for base, ns, off in view_indices(st["in"], A0, A1, N, B, ub_in):
+                    arr, o = mem.resolve(base)
+                    data[:, :, ns, :] = arr[o + off]
+                res = np.fft.ifft(data, axis=2) * N if st["inverse"] else np.fft.fft(data, axis=2)
+                for base, ns, off in view_indices(st["out"], A0, A1, N, B, ub_out):
+                    arr, o = mem.resolve(base)
+                    pending.append((arr, o + off, res[:, :, ns, :]))
+            elif kind == 2:  # R2C: N complex = 2N reals in, N+1 complex out
+                data = np.zeros((A0, A1, N, 1), dtype=np.complex128)
+                for base, ns, off in view_indices(st["in"], A0, A1, N, 1, ub_in):
+                    arr, o = mem.resolve(base)
+                    data[:, :, ns, :] = arr[o + off]
+                reals = np.ascontiguousarray(data[..., 0]).view(np.float64)  # (A0, A1, 2N)
+                res = np.fft.rfft(reals, axis=2)[..., None]
+                for base, ns, off in view_indices(st["out"], A0, A1, N + 1, 1, ub_out):
+                    arr, o = mem.resolve(base)
+                    pending.append((arr, o + off, res[:, :, ns, :]))
+            else:  # C2R
+                data = np.zeros((A0, A1, N + 1, 1), dtype=np.complex128)
+                for base, ns, off in view_indices(st["in"], A0, A1, N + 1, 1, ub_in):
+                    arr, o = mem.resolve(base)
+                    data[:, :, ns, :] = arr[o + off]
+                reals = np.fft.irfft(data[..., 0], n=2 * N, axis=2) * (2 * N)
+                res = np.ascontiguousarray(reals).view(np.complex128)[..., None]
+                for base, ns, off in view_indices(st["out"], A0, A1, N, 1, ub_out):
+                    arr, o = mem.resolve(base)
+                    pending.append((arr, o + off, res[:, :, ns, :]))
+        for arr, idx, val in pending:  # stores of step k land after every rank's loads of step k
+            if isinstance(idx, (int, np.integer)):
+                arr[idx:idx + val.size] = val
+            else:
+                arr[idx] = val
+    worst = 0.0
+    for r in range(P):
+        if not inverse:
+            osz, ost = lay(r, d)
+            got = uout[r][:int(np.prod(osz))].reshape(osz)
+            worst = max(worst, O.rel_l2(got, O.block(spec, ost, osz)))
+        else:
+            isz, ist = lay(r, 0)
+            want = O.block(xg, ist, isz).astype(np.complex128 if c2c else np.float64)
+            scale = float(nz * (ny if d >= 2 else 1) * (nx if d >= 3 else 1))
+            got = uout[r].reshape(isz) if c2c else uout[r].view(np.float64).reshape(isz)
+            worst = max(worst, O.rel_l2(got, want * scale))
+    return worst
+
+
+SL, ZY, PE = dfft.SLAB_ZY_THEN_X, dfft.SLAB_Z_THEN_YX, dfft.PENCIL
+P2P, A2A = 0, 1
+SYNC, STREAMS = 0, 1
+CASES = [
+    # P, decomp, transform, shape, p1, p2, comm, send
+    (1, SL, dfft.C2C, (8, 16, 64), 1, 1, P2P, SYNC),          # blocked hand-over, one rank
+    (4, SL, dfft.C2C, (16, 8, 64), 4, 1, P2P, SYNC),          # blocked hand-over, peer stores
+    (4, SL, dfft.R2C, (16, 8, 32), 4, 1, P2P, SYNC),
+    (3, SL, dfft.R2C, (8, 16, 16), 3, 1, P2P, SYNC),          # uneven split (8 over 3, 16 over 3)
+    (8, SL, dfft.C2C, (16, 16, 64), 8, 1, A2A, SYNC),
+    (8, SL, dfft.R2C, (32, 16, 64), 8, 1, P2P, STREAMS),      # overlapped schedule, R2C (plain layout)
+    (8, SL, dfft.C2C, (32, 16, 256), 8, 1, P2P, STREAMS),     # overlapped + blocked
+    (2, SL, dfft.C2C, (8, 8, 128), 2, 1, P2P, STREAMS),
+    (4, ZY, dfft.R2C, (8, 4, 32), 4, 1, P2P, SYNC),
+    (4, ZY, dfft.C2C, (8, 4, 16), 4, 1, A2A, SYNC),
+    (8, PE, dfft.R2C, (8, 16, 32), 2, 4, P2P, SYNC),
+    (8, PE, dfft.C2C, (16, 8, 16), 4, 2, A2A, SYNC),
+    (6, PE, dfft.R2C, (8, 16, 16), 3, 2, P2P, SYNC),
+    (4, PE, dfft.C2C, (4, 8, 8), 2, 2, P2P, SYNC),
+]
+
+
+@pytest.mark.parametrize("P,decomp,transform,shape,p1,p2,comm,send", CASES)
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_full_schedules(P, decomp, transform, shape, p1, p2, comm, send, inverse):
+    assert run_case(P, decomp, transform, shape, p1, p2, comm, send, inverse, 3) < 1e-12
+
+
+@pytest.mark.parametrize("d", [1, 2])
+@pytest.mark.parametrize("inverse", [0, 1])
+@pytest.mark.parametrize("comm", [P2P, A2A])
+def test_pencil_partial_schedules(d, inverse, comm):
+    assert run_case(8, PE, dfft.R2C, (8, 16, 32), 2, 4, comm, SYNC, inverse, d) < 1e-12
+    assert run_case(4, PE, dfft.C2C, (8, 8, 16), 2, 2, comm, SYNC, inverse, d) < 1e-12
