@@ -212,3 +212,25 @@ def test_cpp_shim_caller(tmp_path):
                     "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + libdir], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_host_executor_pipeline():
+    """HostExecutor: pinned host in -> device -> transform -> pinned host out, pipelined over submits."""
+    shape = (32, 64, 128)
+    plan = make_plan(dfft.MPIcuFFT_Slab, dfft.F64, dfft.R2C, shape)
+    hx = dfft.HostExecutor(plan, dfft.FORWARD)
+    ins = [O.real_input(shape, seed=s) for s in (1, 2, 3, 4, 5)]
+    hin = [torch.from_numpy(a.copy()).pin_memory() for a in ins]
+    hout = [torch.empty(32 * 64 * 65, dtype=torch.complex128).pin_memory() for _ in ins]
+    for o, i in zip(hout, hin):
+        hx.submit(o, i)
+    hx.wait()
+    for o, a in zip(hout, ins):
+        assert O.rel_l2(o.numpy().reshape(32, 64, 65), O.fft_r2c(a)) < 1e-10
+    # inverse through the host path
+    hb = dfft.HostExecutor(plan, dfft.INVERSE)
+    back = torch.empty(32 * 64 * 128, dtype=torch.float64).pin_memory()
+    hb.submit(back, hout[2])
+    hb.wait()
+    assert O.rel_l2(back.numpy().reshape(shape), ins[2] * np.prod(shape)) < 1e-10
+    plan.destroy()
