@@ -84,7 +84,7 @@ struct Shape {
 #define DFFT_TILE_POINTS_F64 4096
 #endif
 #ifndef DFFT_TILE_POINTS_F32
-#define DFFT_TILE_POINTS_F32 8192
+#define DFFT_TILE_POINTS_F32 4096
 #endif
     static constexpr int MINROW = DFFT_MINROW_BYTES / int(2 * sizeof(T));
     static constexpr int WANT = (sizeof(T) == 8 ? DFFT_TILE_POINTS_F64 : DFFT_TILE_POINTS_F32) / N;
@@ -97,6 +97,14 @@ struct Shape {
     // experimental wider tile (DFFT_WIDE_TILES=1): double width if it still fits 128 KB / 1024 threads
     static constexpr int TBT_WIDE = (2 * TBT <= CAP && 2 * TBT <= 32) ? 2 * TBT : TBT;
 };
+
+// Resident CTAs per SM the register allocator must leave room for: 128 registers per thread for f64 and 64 for
+// f32 (16 points per thread) — without it the grid-stride version of the f32 kernels drifted to 90+ registers and
+// lost its second CTA per SM (tiled y pass 5300 -> 3850 GB/s).
+template <typename T>
+constexpr int min_ctas_per_sm(int threads) {
+    return (65536 / (threads * (sizeof(T) == 8 ? 128 : 64))) < 1 ? 1 : (65536 / (threads * (sizeof(T) == 8 ? 128 : 64)));
+}
 
 template <typename T>
 __device__ __forceinline__ cx<T> ld_elem(const cx<T>* p) {
@@ -254,7 +262,7 @@ struct TileCoord {
 // (FftParams::max_ctas) it is persistent and occupies only that many CTA slots, which is how the overlapped
 // schedule leaves the rest of the GPU to the other passes.
 template <typename T, int LOG2N, int LOG2E, int TB, bool TILED, bool INV>
-__global__ void __launch_bounds__((1 << (LOG2N - LOG2E)) * TB)
+__global__ void __launch_bounds__((1 << (LOG2N - LOG2E)) * TB, min_ctas_per_sm<T>((1 << (LOG2N - LOG2E)) * TB))
 fft_c2c_kernel(const __grid_constant__ FftParams p) {
     using C = CtaFft<T, LOG2N, LOG2E, TB, TILED>;
     using LA = LineAccess<T, C::LINES>;
@@ -452,7 +460,7 @@ fft_c2c_pipe_kernel(const __grid_constant__ FftParams p) {
 // The real line is read as M complex points z[m] = x[2m] + i x[2m+1], transformed with the length-M
 // core and split into even/odd spectra in shared memory:  X[k] = Xe[k] + W_2M^k Xo[k].
 template <typename T, int LOG2M, int LOG2E, int TB>
-__global__ void __launch_bounds__((1 << (LOG2M - LOG2E)) * TB)
+__global__ void __launch_bounds__((1 << (LOG2M - LOG2E)) * TB, min_ctas_per_sm<T>((1 << (LOG2M - LOG2E)) * TB))
 fft_r2c_kernel(const __grid_constant__ FftParams p) {
     using C = CtaFft<T, LOG2M, LOG2E, TB, false>;
     using LA = LineAccess<T, C::LINES>;
@@ -508,7 +516,7 @@ fft_r2c_kernel(const __grid_constant__ FftParams p) {
 
 // ---- C2R pass (CONTIG): M+1 complex points -> real line of 2M points, unnormalised -----------------------
 template <typename T, int LOG2M, int LOG2E, int TB>
-__global__ void __launch_bounds__((1 << (LOG2M - LOG2E)) * TB)
+__global__ void __launch_bounds__((1 << (LOG2M - LOG2E)) * TB, min_ctas_per_sm<T>((1 << (LOG2M - LOG2E)) * TB))
 fft_c2r_kernel(const __grid_constant__ FftParams p) {
     using C = CtaFft<T, LOG2M, LOG2E, TB, false>;
     using LA = LineAccess<T, C::LINES>;

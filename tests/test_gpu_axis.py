@@ -70,46 +70,40 @@ def test_strided_c2c(prec, a, n, b):
     assert O.rel_l2(host(buf), np.fft.fft(x.astype(np.complex128), axis=1)) < TOL[prec]
 
 
-@pytest.mark.parametrize("env", [{"DFFT_WIDE_TILES": "1"}, {"DFFT_PIPE": "1"}, {"DFFT_PIPE": "1", "DFFT_WIDE_TILES": "1"}])
-def test_kernel_variants(env):
+@pytest.mark.parametrize("env", [{"DFFT_WIDE_TILES": "1"}, {"DFFT_PIPE": "1"}, {"DFFT_PIPE": "1", "DFFT_WIDE_TILES": "1"}, {"DFFT_WIDE_TILES": "-1"}])
+def test_kernel_variants(env, monkeypatch):
     """The alternative kernel variants (wide tiles, persistent register-prefetch) are selected by environment
-    variables read once per process, so they are checked in a subprocess."""
-    import os
-    import subprocess
-    import sys
-    code = r'''
-import numpy as np, torch, sys
-sys.path.insert(0, "tests"); sys.path.insert(0, ".")
-import distributedfft_b200 as dfft
-from oracle import dft_oracle as O
-worst = 0.0
-for prec, cdt, tol in ((dfft.F64, np.complex128, 1e-10), (dfft.F32, np.complex64, 1e-5)):
-    for (a, n, b) in ((2, 1024, 37), (1, 2048, 16), (3, 256, 40), (1, 512, 129), (2, 128, 64)):
-        rng = np.random.default_rng(n)
-        x = (rng.standard_normal((a, n, b)) + 1j * rng.standard_normal((a, n, b))).astype(cdt)
-        xin = torch.from_numpy(x).cuda(); out = torch.empty_like(xin)
-        for d in (dfft.FORWARD, dfft.INVERSE):
-            dfft.fft1d_strided(prec, d, a, n, b, out, xin); torch.cuda.synchronize()
-            ref = np.fft.fft(x.astype(np.complex128), axis=1) if d == dfft.FORWARD else np.fft.ifft(x.astype(np.complex128), axis=1) * n
-            e = O.rel_l2(out.cpu().numpy(), ref); worst = max(worst, e / tol)
-    for n in (64, 1024, 4096):
-        lines = 77
-        rng = np.random.default_rng(n)
-        x = (rng.standard_normal((lines, n)) + 1j * rng.standard_normal((lines, n))).astype(cdt)
-        xin = torch.from_numpy(x).cuda(); out = torch.empty_like(xin)
-        dfft.fft1d_contig(prec, 0, dfft.FORWARD, n, lines, out, n, xin, n); torch.cuda.synchronize()
-        e = O.rel_l2(out.cpu().numpy(), np.fft.fft(x.astype(np.complex128), axis=1)); worst = max(worst, e / tol)
-    shape = (64, 1024, 32)
-    plan = dfft.MPIcuFFT_Slab(dfft.Configurations(), dfft.Comm(), precision="double" if prec == dfft.F64 else "float", transform="c2c")
-    plan.initFFT(dfft.GlobalSize(*shape), None, True)
-    xc = O.complex_input(shape, dtype=cdt); outc = torch.empty(shape, dtype=torch.complex128 if prec == dfft.F64 else torch.complex64, device="cuda")
-    plan.execC2C(outc, torch.from_numpy(xc).cuda(), dfft.FORWARD)
-    worst = max(worst, O.rel_l2(outc.cpu().numpy(), O.fft_c2c(xc)) / tol)
-print("WORST", worst)
-assert worst < 1.0
-'''
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    e = dict(os.environ)
-    e.update(env)
-    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=e, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    variables that the launcher reads at every launch."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    worst = 0.0
+    for prec in (dfft.F64, dfft.F32):
+        tol = TOL[prec]
+        for (a, n, b) in ((2, 1024, 37), (1, 2048, 16), (3, 256, 40), (1, 512, 129), (2, 128, 64)):
+            rng = np.random.default_rng(n)
+            x = (rng.standard_normal((a, n, b)) + 1j * rng.standard_normal((a, n, b))).astype(NPC[prec])
+            xin = dev(x)
+            out = torch.empty_like(xin)
+            for d in (dfft.FORWARD, dfft.INVERSE):
+                dfft.fft1d_strided(prec, d, a, n, b, out, xin)
+                torch.cuda.synchronize()
+                ref = np.fft.fft(x.astype(np.complex128), axis=1) if d == dfft.FORWARD else np.fft.ifft(x.astype(np.complex128), axis=1) * n
+                worst = max(worst, O.rel_l2(host(out), ref) / tol)
+        for n in (64, 1024, 4096):
+            lines = 77
+            rng = np.random.default_rng(n)
+            x = (rng.standard_normal((lines, n)) + 1j * rng.standard_normal((lines, n))).astype(NPC[prec])
+            xin = dev(x)
+            out = torch.empty_like(xin)
+            dfft.fft1d_contig(prec, 0, dfft.FORWARD, n, lines, out, n, xin, n)
+            torch.cuda.synchronize()
+            worst = max(worst, O.rel_l2(host(out), np.fft.fft(x.astype(np.complex128), axis=1)) / tol)
+        shape = (64, 1024, 32)
+        plan = dfft.MPIcuFFT_Slab(dfft.Configurations(), dfft.Comm(), precision="double" if prec == dfft.F64 else "float", transform="c2c")
+        plan.initFFT(dfft.GlobalSize(*shape), None, True)
+        xc = O.complex_input(shape, dtype=NPC[prec])
+        outc = torch.empty(shape, dtype=CDT[prec], device="cuda")
+        plan.execC2C(outc, dev(xc), dfft.FORWARD)
+        worst = max(worst, O.rel_l2(host(outc), O.fft_c2c(xc)) / tol)
+        plan.destroy()
+    assert worst < 1.0
