@@ -327,22 +327,32 @@ def main(argv=None):
     fft_ms = bd_avg["fft_ms"]
     tot_bytes = sum(q["algorithmic_bytes"] for q in passes)
     dom = max(passes, key=lambda q: q["ms"])
-    roofline = {"bound": "hbm", "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["frac"], "traffic": None,
+    # DRAM bytes per launch of a pass, from the ncu --set full capture of exactly this launch shape
+    # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r01b_passes_n512_f64_ncu_full.csv): 2^27 f64 points
+    traffic = 2.1476e9 + 2.0993e9 if (f64 and c2c and int(ntot_local) == 2 ** 27 and world == 1) else None
+    roofline = {"bound": "hbm", "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["frac"], "traffic": traffic,
                 "peak_source": peak_src, "kernel": f"dominant FFT pass: {dom['step']} ({dom['ms']:.3f} ms per launch; algorithmic bytes = one read + one write of the local array)",
                 "all_passes": passes, "all_passes_achieved": tot_bytes / (fft_ms * 1e-3) / 1e9, "all_passes_frac": tot_bytes / (fft_ms * 1e-3) / 1e9 / hbm_peak,
                 "fft_ms": fft_ms, "exchange_ms": bd_avg["exchange_ms"], "steps_ms": dict(zip([f"{i}:{l}" for i, l in enumerate(labels)], step_ms)),
                 "phases_cumulative_ms": dict(zip(names, cum))}
     if world > 1:
-        sent = cplx_bytes * (world - 1) / world
-        # Peer2Peer: the scattering pass IS the transfer; All2All: the NCCL step is
-        xfer = [ms for lab, ms in zip(labels, step_ms) if "all-to-all" in lab]
-        if not xfer:
-            xfer = [q["ms"] for q in passes if q["step"] == "y pass"]
-        t_x = max(xfer) if xfer else None
-        roofline["nvlink"] = {"bytes_sent_per_gpu": sent, "transfer_ms": t_x, "gbs_per_direction": (sent / (t_x * 1e-3) / 1e9) if t_x else None,
-                              "peak_nominal": 900.0, "peak_measured_peer_copy": 770.0,
-                              "eff_vs_nominal": (sent / (t_x * 1e-3) / 1e9 / 900.0) if t_x else None,
-                              "note": "Peer2Peer: the y pass stores straight into the peers' slots, so its duration is the transfer time"}
+        def link(sent, t_x, note):
+            return {"bytes_sent_per_gpu": sent, "transfer_ms": t_x, "gbs_per_direction": (sent / (t_x * 1e-3) / 1e9) if t_x else None,
+                    "peak_nominal": 900.0, "peak_measured_peer_copy": 770.0, "eff_vs_nominal": (sent / (t_x * 1e-3) / 1e9 / 900.0) if t_x else None,
+                    "note": note}
+        a2a = [ms for lab, ms in zip(labels, step_ms) if "all-to-all" in lab]
+        pass_ms = {q["step"]: q["ms"] for q in passes}
+        if args.decomp == "pencil":
+            p1 = args.p1 or 2
+            p2 = args.p2 or world // p1
+            t1 = a2a[0] if a2a else next((ms for lab, ms in pass_ms.items() if lab.startswith("z pass")), None)
+            t2 = a2a[1] if len(a2a) > 1 else pass_ms.get("y pass")
+            roofline["nvlink"] = [link(cplx_bytes * (p2 - 1) / p2, t1, "first transposition (row group): scattered by the z pass (Peer2Peer) or NCCL step"),
+                                  link(cplx_bytes * (p1 - 1) / p1, t2, "second transposition (column group): scattered by the y pass (Peer2Peer) or NCCL step")]
+        else:
+            t_x = max(a2a) if a2a else (pass_ms.get("y pass") if args.decomp == "slab" else next((ms for lab, ms in pass_ms.items() if lab.startswith("z pass")), None))
+            roofline["nvlink"] = link(cplx_bytes * (world - 1) / world, t_x,
+                                      "Peer2Peer: the scattering pass stores straight into the peers' slots, so its duration is the transfer time")
 
     # end-to-end through the public host-buffer API (HostExecutor): every step copies its input block from pinned
     # host memory, transforms it and copies the spectrum block back; consecutive steps are pipelined (the D2H of

@@ -40,7 +40,7 @@ def main():
                 d = json.loads(line)
                 r = d["roofline"]
                 print(name, "ms", round(d["ms_per_step"], 3), "GFLOP/s", round(d["value"]), "seq_ms", round(d["config"]["sequential_schedule_ms"], 3),
-                      "steps", {k: round(v, 3) for k, v in r["steps_ms"].items()}, "nvlink_GB/s", r.get("nvlink", {}).get("gbs_per_direction"), flush=True)
+                      "steps", {k: round(v, 3) for k, v in r["steps_ms"].items()}, "nvlink", [x.get("gbs_per_direction") for x in (r["nvlink"] if isinstance(r.get("nvlink"), list) else [r.get("nvlink", {})])], flush=True)
         except Exception as ex:  # keep going: the box is expensive
             if rank == 0:
                 print(name, "FAILED", repr(ex), flush=True)
