@@ -73,3 +73,22 @@ def test_argument_errors_have_codes_and_messages():
     assert l.dfft_partition(8, 0, size, start) == -1
     with pytest.raises(_lib.DfftError):
         _lib.check(l.dfft_exec_r2c(None, None, None))
+
+
+def test_job_runner_maps_reference_job_files():
+    """tests/launch_jobs.py turns the reference's job JSON (launch.py schema) into torchrun + cli.py commands."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("launch_jobs", os.path.join(ROOT, "tests", "launch_jobs.py"))
+    lj = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(lj)
+    job = {"size": [128, [128, 128, 256]], "global_test_settings": {"$-t": 4, "--warmup-rounds": 1, "--iterations": 0, "--double_prec": True},
+           "tests": [{"name": "Slab", "-comm": "Peer2Peer", "-snd": "Streams", "--cuda_aware": False, "-p": 4},
+                     {"name": "Pencil", "-comm": "All2All", "-snd": "Sync", "-p1": 2, "-p2": 2},
+                     {"name": "Reference", "-t": 2, "-p1": 2, "-p2": 2}]}
+    cmds = list(lj.commands(job, 4))
+    assert len(cmds) == 4
+    first = " ".join(cmds[0])
+    assert "--nproc-per-node=4" in first and "cli.py slab" in first and "-comm Peer2Peer" in first and "-snd Streams" in first
+    assert "-t 4" in first and "-d" in cmds[0] and "-c" not in cmds[0] and "-nx 128" in first and "-w 1" in first
+    assert "-nz 256" in " ".join(cmds[1])
+    assert "cli.py pencil" in " ".join(cmds[2]) and "-p1 2" in " ".join(cmds[2])
