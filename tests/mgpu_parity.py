@@ -16,11 +16,71 @@ import distributedfft_b200 as dfft  # noqa: E402
 from oracle import dft_oracle as O  # noqa: E402
 
 
+def full_size_properties(comm, rank, world):
+    """BASELINE configs 3-5 at full size, checked through size-independent properties (no global array on any
+    rank): forward -> inverse round trip, Parseval, DC bin.  Weak-scaling shapes below 8 ranks."""
+    shapes = {1: (512, 512, 512), 2: (1024, 512, 512), 4: (1024, 1024, 512), 8: (1024, 1024, 1024)}
+    shape = shapes.get(world, (512, 512, 512))
+    n = float(np.prod(shape))
+    fails = 0
+    cases = [("slab c2c f64 Streams", dfft.MPIcuFFT_Slab, None, "double", "c2c", dfft.SendMethod.Streams, shape),
+             ("slab r2c f64 Streams", dfft.MPIcuFFT_Slab, None, "double", "r2c", dfft.SendMethod.Streams, shape),
+             ("slab r2c f64 Sync All2All", dfft.MPIcuFFT_Slab, None, "double", "r2c", "a2a", shape)]
+    if world == 8:
+        cases.append(("pencil 2x4 c2c f32", dfft.MPIcuFFT_Pencil, (2, 4), "float", "c2c", dfft.SendMethod.Sync, (2048, 2048, 1024)))
+    for name, cls, grid, prec, tr, snd, shp in cases:
+        a2a = snd == "a2a"
+        cm = dfft.CommunicationMethod.All2All if a2a else dfft.CommunicationMethod.Peer2Peer
+        cfg = dfft.Configurations(comm_method=cm, comm_method2=cm, send_method=dfft.SendMethod.Sync if a2a else snd)
+        plan = cls(cfg, comm, precision=prec, transform=tr)
+        plan.initFFT(dfft.GlobalSize(*shp), dfft.Pencil_Partition(*grid) if grid else None, True)
+        f64 = prec == "double"
+        rdt, cdt = (torch.float64, torch.complex128) if f64 else (torch.float32, torch.complex64)
+        tol = 1e-10 if f64 else 1e-5
+        isz, osz = plan.getInSize(), plan.getOutSize()
+        nt = float(np.prod(shp))
+        g = torch.Generator(device="cuda").manual_seed(100 + rank)
+        if tr == "c2c":
+            x = torch.complex(torch.rand(isz, generator=g, device="cuda", dtype=rdt), torch.rand(isz, generator=g, device="cuda", dtype=rdt))
+        else:
+            x = torch.rand(isz, generator=g, device="cuda", dtype=rdt)
+        dom = plan.getDomainSize() // (16 if f64 else 8)
+        out = torch.empty(dom, dtype=cdt, device="cuda")
+        back = torch.empty_like(x)
+        if tr == "c2c":
+            plan.execC2C(out, x, dfft.FORWARD)
+            n_out = osz[0] * osz[1] * osz[2]
+            e = torch.stack([(x.abs().double() ** 2).sum(), (out[:n_out].abs().double() ** 2).sum()])
+            dist.all_reduce(e)
+            parseval = abs(float(e[1]) / (nt * float(e[0])) - 1.0)
+            plan.execC2C(back, out, dfft.INVERSE)
+        else:
+            plan.execR2C(out, x)
+            parseval = 0.0
+            plan.execC2R(back, out)
+        err = torch.tensor([float((back / nt - x).abs().max())], device="cuda", dtype=torch.float64)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        ok = float(err) < tol and parseval < tol
+        fails += 0 if ok else 1
+        if rank == 0:
+            print(f"{'ok  ' if ok else 'FAIL'} full-size {name} {shp}: roundtrip max err {float(err):.2e}, parseval {parseval:.2e}", flush=True)
+        del x, out, back
+        plan.destroy()
+        torch.cuda.empty_cache()
+    return fails
+
+
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     comm = dfft.Comm.from_torch_distributed(local)
+    if "--full" in sys.argv:
+        fails = full_size_properties(comm, rank, world)
+        if rank == 0:
+            print(f"mgpu_parity --full: {fails} failed", flush=True)
+        dist.destroy_process_group()
+        sys.exit(1 if fails else 0)
     quick = "--quick" in sys.argv
     grids = [(1, world), (world, 1)] + ([(2, world // 2)] if world >= 4 else [])
     cases = []
