@@ -245,6 +245,7 @@ struct dfft_plan_s {
     cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
     int xchg_ctas = 0;                            // SMs given to the exchange pass in overlapped schedules
     int blocked_ch = 0;                           // > 0: slab forward keeps the y->x intermediate as [b/CH][Nx][CH]
+    int xchg_tile_pref = 2;                       // tile preference of passes that store into other GPUs (2 = wide rows)
     cudaStream_t own_stream = nullptr, last_stream = nullptr;  // last_stream: stream of the last exec
     Tables tabs;
     // schedules: [fwd/inv][d-1]
@@ -520,13 +521,14 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
             // blocked hand-over: receiver q holds [(ny_q*nzc)/CH][nx][CH]
             s2.prm.A1 = int(nz_j / CH); s2.prm.B = int(CH);
             s2.prm.in.seg[0].sA1 = (long long)CH;
-            s2.prm.tile_pref = 1;
+            s2.prm.tile_pref = G2.size() > 1 ? p->xchg_tile_pref : 1;
             seg_view(s2.prm.out, tab_y_out, G2, [&](int, int r) {
                 SegN sn = mkseg(eptr(slotp(D2, r), x0_i * CH, es), (long long)CH, (long long)(g.nx * CH), (long long)(nz_j * g.nx), 0);
                 return sn;
             });
             for (size_t q = 0; q < G2.size(); ++q) s2.prm.out.seg[q].n0 = int(g.oy.start[q]);
         } else if (dir2) {
+            if (G2.size() > 1) s2.prm.tile_pref = p->xchg_tile_pref;
             seg_view(s2.prm.out, tab_y_out, G2, [&](int q, int r) {
                 const size_t nyq = g.oy.size[q];
                 return mkseg(eptr(slotp(D2, r), x0_i * nyq * nz_j, es), (long long)(nyq * nz_j), 0, (long long)nz_j, g.oy.start[q]);
@@ -645,6 +647,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
         s3.prm.A0 = 1; s3.prm.A1 = 1; s3.prm.B = int(oy_i * nz_j);
         s3.prm.in = single_view(nullptr, 0, 0, (long long)(oy_i * nz_j));
         s3.in_user = 1;
+        if (dir2 && G2.size() > 1) s3.prm.tile_pref = p->xchg_tile_pref;
         if (dir2) {
             // dest (q,j) holds [nx_q][ny][nz_j]; my rows y in [oy0_i, +oy_i)
             seg_view(s3.prm.out, tab_x, G2, [&](int q, int r) {
@@ -679,6 +682,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
         });
     }
     Step x1;
+    if (dir1 && G1.size() > 1) s2.prm.tile_pref = p->xchg_tile_pref;
     if (dir1) {
         // dest (i,q) holds [nx_i][ny_q][nzc]; my columns z in [z0_j, +nz_j)
         seg_view(s2.prm.out, tab_y_in, G1, [&](int q, int r) {
@@ -825,13 +829,14 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
                 if (CH) {
                     s.prm.A0 = int(npl); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
                     s.prm.in = single_view(eptr(slotp(D1, me), pl0 * ny * nzc + z0, es), (long long)(ny * nzc), (long long)CH, (long long)nzc);
-                    s.prm.tile_pref = 1;
+                    s.prm.tile_pref = p->xchg_tile_pref;
                     seg_view(s.prm.out, tab_y, G2, [&](int, int r) {
                         return mkseg(eptr(slotp(D2, r), (x0 + pl0) * CH + (z0 / CH) * nx * CH, es), (long long)CH, (long long)(nx * CH), (long long)(nzc * nx), 0);
                     });
                     for (size_t q = 0; q < G2.size(); ++q) s.prm.out.seg[q].n0 = int(g.oy.start[q]);
                 } else {
                 s.prm.A0 = int(npl); s.prm.A1 = 1; s.prm.B = int(zc);
+                s.prm.tile_pref = p->xchg_tile_pref;
                 s.prm.in = single_view(eptr(slotp(D1, me), pl0 * ny * nzc + z0, es), (long long)(ny * nzc), 0, (long long)nzc);
                 seg_view(s.prm.out, tab_y, G2, [&](int q, int r) {
                     const size_t nyq = g.oy.size[q];
@@ -883,6 +888,7 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
                 return mkseg(eptr(slotp(D2, r), oy0_me * nzc + z0, es), 0, (long long)nzc, (long long)(ny * nzc), g.sx.start[q]);
             });
             s.prm.max_ctas = p->xchg_ctas;
+            s.prm.tile_pref = p->xchg_tile_pref;
             s.stream = 1;
             if (c == 0) s.waits.push_back(ev_entry);
             s.record = ev_x[c] = nev++;
@@ -1368,6 +1374,11 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         // Blocked intermediate layout for the slab's y -> x hand-over: [b/CH][Nx][CH] makes every x-pass tile a
         // compact block instead of Nx rows in Nx different 2 MB pages (x pass +14..16 %, y pass -3 %,
         // tools/layout_probe.py).  Needs CH | Nzc, i.e. complex plans with power-of-two Nz.  DFFT_BLOCKED=0 disables.
+        // NVLink store efficiency grows with the contiguous run per row: 64-byte rows reach 434 GB/s per direction,
+        // 128-byte rows 700 GB/s, 2 KB runs 704 GB/s (profiles/r01_8gpu, r01_bench_n2_*): exchanging passes prefer the
+        // wide tile even though it is slower as a purely local pass.  DFFT_XCHG_WIDE=0 keeps the narrow tile.
+        const char* ew = getenv("DFFT_XCHG_WIDE");
+        p->xchg_tile_pref = (ew && atoi(ew) == 0) ? 1 : 2;
         const char* eb = getenv("DFFT_BLOCKED");
         const int ch = eb ? atoi(eb) : 16;
         p->blocked_ch = (decomp == DFFT_SLAB_ZY_THEN_X && ch > 0 && g.nzc % size_t(ch) == 0 && g.nzc >= size_t(4 * ch)) ? ch : 0;
