@@ -518,15 +518,15 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
         const bool t2_a2a = !dir2;
         const size_t CH = (dir2 && g.decomp == DFFT_SLAB_ZY_THEN_X && !(t1_a2a)) ? size_t(p->blocked_ch) : 0;
         if (dir2 && CH) {
-            // blocked hand-over: receiver q holds [(ny_q*nzc)/CH][nx][CH]
+            // blocked hand-over: receiver q holds [nzc/CH][nx][ny_q][CH] — the rows a y-pass tile sends to one
+            // destination (consecutive y) are adjacent, so every warp store is 512 contiguous bytes
             s2.prm.A1 = int(nz_j / CH); s2.prm.B = int(CH);
             s2.prm.in.seg[0].sA1 = (long long)CH;
-            s2.prm.tile_pref = G2.size() > 1 ? p->xchg_tile_pref : 1;
-            seg_view(s2.prm.out, tab_y_out, G2, [&](int, int r) {
-                SegN sn = mkseg(eptr(slotp(D2, r), x0_i * CH, es), (long long)CH, (long long)(g.nx * CH), (long long)(nz_j * g.nx), 0);
-                return sn;
+            s2.prm.tile_pref = 1;
+            seg_view(s2.prm.out, tab_y_out, G2, [&](int q, int r) {
+                const size_t nyq = g.oy.size[q];
+                return mkseg(eptr(slotp(D2, r), x0_i * nyq * CH, es), (long long)(nyq * CH), (long long)(g.nx * nyq * CH), (long long)CH, g.oy.start[q]);
             });
-            for (size_t q = 0; q < G2.size(); ++q) s2.prm.out.seg[q].n0 = int(g.oy.start[q]);
         } else if (dir2) {
             if (G2.size() > 1) s2.prm.tile_pref = p->xchg_tile_pref;
             seg_view(s2.prm.out, tab_y_out, G2, [&](int q, int r) {
@@ -551,9 +551,10 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
         if (rc) return rc;
         s3.label = "x pass";
         if (CH) {
-            s3.prm.A0 = 1; s3.prm.A1 = int(oy_i * nz_j / CH); s3.prm.B = int(CH);
-            s3.prm.in = single_view(slotp(D2, me), 0, (long long)(g.nx * CH), (long long)CH);
-            s3.prm.out = single_view(nullptr, 0, (long long)CH, (long long)(oy_i * nz_j));
+            // in: [nzc/CH][nx][oy_i][CH]: a0 = y_loc, a1 = z chunk, n = x
+            s3.prm.A0 = int(oy_i); s3.prm.A1 = int(nz_j / CH); s3.prm.B = int(CH);
+            s3.prm.in = single_view(slotp(D2, me), (long long)CH, (long long)(g.nx * oy_i * CH), (long long)(oy_i * CH));
+            s3.prm.out = single_view(nullptr, (long long)nz_j, (long long)CH, (long long)(oy_i * nz_j));
         } else {
             s3.prm.A0 = 1; s3.prm.A1 = 1; s3.prm.B = int(oy_i * nz_j);
             s3.prm.in = single_view(t2_a2a ? slotp(SR, me) : slotp(D2, me), 0, 0, (long long)(oy_i * nz_j));
@@ -829,11 +830,12 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
                 if (CH) {
                     s.prm.A0 = int(npl); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
                     s.prm.in = single_view(eptr(slotp(D1, me), pl0 * ny * nzc + z0, es), (long long)(ny * nzc), (long long)CH, (long long)nzc);
-                    s.prm.tile_pref = p->xchg_tile_pref;
-                    seg_view(s.prm.out, tab_y, G2, [&](int, int r) {
-                        return mkseg(eptr(slotp(D2, r), (x0 + pl0) * CH + (z0 / CH) * nx * CH, es), (long long)CH, (long long)(nx * CH), (long long)(nzc * nx), 0);
+                    s.prm.tile_pref = 1;
+                    seg_view(s.prm.out, tab_y, G2, [&](int q, int r) {
+                        const size_t nyq = g.oy.size[q];
+                        return mkseg(eptr(slotp(D2, r), ((z0 / CH) * nx + x0 + pl0) * nyq * CH, es), (long long)(nyq * CH), (long long)(nx * nyq * CH),
+                                     (long long)CH, g.oy.start[q]);
                     });
-                    for (size_t q = 0; q < G2.size(); ++q) s.prm.out.seg[q].n0 = int(g.oy.start[q]);
                 } else {
                 s.prm.A0 = int(npl); s.prm.A1 = 1; s.prm.B = int(zc);
                 s.prm.tile_pref = p->xchg_tile_pref;
@@ -860,9 +862,9 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
             rc = new_pass(PASS_C2C_TILED, nx, "x pass", s);
             if (rc) return rc;
             if (CH) {
-                // in: [(y_loc*(nzc/CH) + zc)][nx][CH]; a0 = y_loc, a1 = zc within this chunk
+                // in: [nzc/CH][nx][oy_me][CH]; a0 = y_loc, a1 = z chunk within this z range, n = x
                 s.prm.A0 = int(oy_me); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
-                s.prm.in = single_view(eptr(slotp(D2, me), (z0 / CH) * nx * CH, es), (long long)((nzc / CH) * nx * CH), (long long)(nx * CH), (long long)CH);
+                s.prm.in = single_view(eptr(slotp(D2, me), (z0 / CH) * nx * oy_me * CH, es), (long long)CH, (long long)(nx * oy_me * CH), (long long)(oy_me * CH));
                 s.prm.out = single_view((void*)(size_t)(z0 * es), (long long)nzc, (long long)CH, (long long)(oy_me * nzc));
             } else {
             s.prm.A0 = 1; s.prm.A1 = int(oy_me); s.prm.B = int(zc);
@@ -1371,16 +1373,17 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
     {
         const char* e = getenv("DFFT_XCHG_CTAS");
         p->xchg_ctas = e ? atoi(e) : 128;
-        // Blocked intermediate layout for the slab's y -> x hand-over: [b/CH][Nx][CH] makes every x-pass tile a
-        // compact block instead of Nx rows in Nx different 2 MB pages (x pass +14..16 %, y pass -3 %,
-        // tools/layout_probe.py).  Needs CH | Nzc, i.e. complex plans with power-of-two Nz.  DFFT_BLOCKED=0 disables.
+        // Blocked intermediate layout for the slab's y -> x hand-over: [Nzc/CH][Nx][Ny_q][CH].  The rows a y-pass tile
+        // sends to one destination are adjacent (512-byte warp stores instead of 64-byte rows: what NVLink needs),
+        // and the x pass reads rows 16 KB apart instead of one row per 2 MB page (tools/layout_probe.py).
+        // Needs CH | Nzc, i.e. complex plans with power-of-two Nz.  DFFT_BLOCKED=0 disables.
         // NVLink store efficiency grows with the contiguous run per row: 64-byte rows reach 434 GB/s per direction,
         // 128-byte rows 700 GB/s, 2 KB runs 704 GB/s (profiles/r01_8gpu, r01_bench_n2_*): exchanging passes prefer the
         // wide tile even though it is slower as a purely local pass.  DFFT_XCHG_WIDE=0 keeps the narrow tile.
         const char* ew = getenv("DFFT_XCHG_WIDE");
         p->xchg_tile_pref = (ew && atoi(ew) == 0) ? 1 : 2;
         const char* eb = getenv("DFFT_BLOCKED");
-        const int ch = eb ? atoi(eb) : 16;
+        const int ch = eb ? atoi(eb) : 8;
         p->blocked_ch = (decomp == DFFT_SLAB_ZY_THEN_X && ch > 0 && g.nzc % size_t(ch) == 0 && g.nzc >= size_t(4 * ch)) ? ch : 0;
     }
     if (dry) {
