@@ -316,7 +316,7 @@ def main(argv=None):
     real_bytes = (es // 2) * ntot_local
     passes = []
     for lab, ms in zip(labels, step_ms):
-        if "pass" not in lab:
+        if "pass" not in lab or "tail" in lab:
             continue
         if lab.startswith("z pass") and not c2c:
             b = real_bytes + cplx_bytes          # R2C: read reals, write Nz/2+1 complex

@@ -517,16 +517,34 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
         Step x2;
         const bool t2_a2a = !dir2;
         const size_t CH = (dir2 && g.decomp == DFFT_SLAB_ZY_THEN_X && !(t1_a2a)) ? size_t(p->blocked_ch) : 0;
+        const size_t rem = CH ? nz_j % CH : 0, nzm = nz_j - rem;
+        Step s2t;
+        bool have_tail = false;
         if (dir2 && CH) {
             // blocked hand-over: receiver q holds [nzc/CH][nx][ny_q][CH] — the rows a y-pass tile sends to one
             // destination (consecutive y) are adjacent, so every warp store is 512 contiguous bytes
-            s2.prm.A1 = int(nz_j / CH); s2.prm.B = int(CH);
+            s2.prm.A1 = int(nzm / CH); s2.prm.B = int(CH);
             s2.prm.in.seg[0].sA1 = (long long)CH;
-            s2.prm.tile_pref = 1;
+            // rows are only adjacent when the tile is CH wide: with remote peers take the wide tile (TB = CH = 8 for
+            // the 1024-point f64 pass; measured 449 -> 700 GB/s per direction), locally the faster narrow one
+            s2.prm.tile_pref = G2.size() > 1 ? p->xchg_tile_pref : 1;
             seg_view(s2.prm.out, tab_y_out, G2, [&](int q, int r) {
                 const size_t nyq = g.oy.size[q];
                 return mkseg(eptr(slotp(D2, r), x0_i * nyq * CH, es), (long long)(nyq * CH), (long long)(g.nx * nyq * CH), (long long)CH, g.oy.start[q]);
             });
+            if (rem) {  // leftover columns z in [nzm, nzc): plain layout [nx][ny_q][rem] behind the blocked part
+                s2t = s2;
+                have_tail = true;
+                s2t.label = "y pass (tail)";
+                s2t.phase = nullptr;
+                s2t.prm.A1 = 1; s2t.prm.B = int(rem);
+                s2t.prm.in.seg[0].base = eptr(s2.prm.in.seg[0].base, nzm, es);
+                s2t.prm.in.seg[0].sA1 = 0;
+                seg_view(s2t.prm.out, tab_y_out, G2, [&](int q, int r) {
+                    const size_t nyq = g.oy.size[q];
+                    return mkseg(eptr(slotp(D2, r), g.nx * nyq * nzm + x0_i * nyq * rem, es), (long long)(nyq * rem), 0, (long long)rem, g.oy.start[q]);
+                });
+            }
         } else if (dir2) {
             if (G2.size() > 1) s2.prm.tile_pref = p->xchg_tile_pref;
             seg_view(s2.prm.out, tab_y_out, G2, [&](int q, int r) {
@@ -540,7 +558,8 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
                 return mkseg(eptr(slotp(SS, me), x2.soff[q], es), (long long)(nyq * nz_j), 0, (long long)nz_j, g.oy.start[q]);
             });
         }
-        sc.steps.push_back(s2);
+        if (have_tail) { const char* ph = s2.phase; s2.phase = nullptr; sc.steps.push_back(s2); s2t.phase = ph; sc.steps.push_back(s2t); }
+        else sc.steps.push_back(s2);
         const bool slab = g.decomp == DFFT_SLAB_ZY_THEN_X;
         if (t2_a2a) { x2.phase = slab ? "Transpose (Finished All2All)" : "Second Transpose (Finished All2All)"; x2.group = 2; sc.steps.push_back(x2); }
         else if (G2.size() > 1) rendezvous(2, 2, slab ? "Transpose (Finished Receive)" : "Second Transpose (Finished Receive)");
@@ -552,9 +571,19 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
         s3.label = "x pass";
         if (CH) {
             // in: [nzc/CH][nx][oy_i][CH]: a0 = y_loc, a1 = z chunk, n = x
-            s3.prm.A0 = int(oy_i); s3.prm.A1 = int(nz_j / CH); s3.prm.B = int(CH);
+            s3.prm.A0 = int(oy_i); s3.prm.A1 = int(nzm / CH); s3.prm.B = int(CH);
             s3.prm.in = single_view(slotp(D2, me), (long long)CH, (long long)(g.nx * oy_i * CH), (long long)(oy_i * CH));
             s3.prm.out = single_view(nullptr, (long long)nz_j, (long long)CH, (long long)(oy_i * nz_j));
+            if (rem) {
+                Step s3t = s3;
+                s3t.label = "x pass (tail)";
+                s3t.phase = nullptr;
+                s3t.prm.A0 = int(oy_i); s3t.prm.A1 = 1; s3t.prm.B = int(rem);
+                s3t.prm.in = single_view(eptr(slotp(D2, me), g.nx * oy_i * nzm, es), (long long)rem, 0, (long long)(oy_i * rem));
+                s3t.prm.out = single_view((void*)(size_t)(nzm * es), (long long)nz_j, 0, (long long)(oy_i * nz_j));
+                s3t.out_user = 2;
+                sc.steps.push_back(s3t);
+            }
         } else {
             s3.prm.A0 = 1; s3.prm.A1 = 1; s3.prm.B = int(oy_i * nz_j);
             s3.prm.in = single_view(t2_a2a ? slotp(SR, me) : slotp(D2, me), 0, 0, (long long)(oy_i * nz_j));
@@ -785,9 +814,10 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
     const size_t NS = nzc >= 128 ? 4 : (nzc >= 32 ? 2 : 1);
     groups.make(nx_p, NG);
     const size_t CH = inverse ? 0 : size_t(p->blocked_ch);
-    if (CH) {  // z chunks are whole multiples of the block width
+    const size_t rem = CH ? nzc % CH : 0, nzm = nzc - rem;
+    if (CH) {  // z chunks are whole multiples of the block width; the Nzc % CH leftover columns ride with the last chunk
         Split u;
-        u.make(nzc / CH, std::min<size_t>(NS, nzc / CH));
+        u.make(nzm / CH, std::min<size_t>(NS, nzm / CH));
         chunks.size.clear(); chunks.start.clear();
         for (size_t c = 0; c < u.size.size(); ++c) { chunks.size.push_back(u.size[c] * CH); chunks.start.push_back(u.start[c] * CH); }
     } else {
@@ -830,7 +860,7 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
                 if (CH) {
                     s.prm.A0 = int(npl); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
                     s.prm.in = single_view(eptr(slotp(D1, me), pl0 * ny * nzc + z0, es), (long long)(ny * nzc), (long long)CH, (long long)nzc);
-                    s.prm.tile_pref = 1;
+                    s.prm.tile_pref = p->xchg_tile_pref;
                     seg_view(s.prm.out, tab_y, G2, [&](int q, int r) {
                         const size_t nyq = g.oy.size[q];
                         return mkseg(eptr(slotp(D2, r), ((z0 / CH) * nx + x0 + pl0) * nyq * CH, es), (long long)(nyq * CH), (long long)(nx * nyq * CH),
@@ -849,8 +879,23 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
                 s.stream = 1;
                 if (c == 0) s.waits.push_back(ev_z[gi]);
                 if (c == 0 && gi == 0) s.waits.push_back(ev_entry);
-                if (gi + 1 == NG) s.record = ev_y[c] = nev++;
+                const bool tail_here = CH && rem && c + 1 == NSc;
+                if (gi + 1 == NG && !tail_here) s.record = ev_y[c] = nev++;
                 sc.steps.push_back(s);
+                if (tail_here) {
+                    Step t = s;
+                    t.label = "y pass (tail)";
+                    t.waits.clear();
+                    t.record = -1;
+                    t.prm.A0 = int(npl); t.prm.A1 = 1; t.prm.B = int(rem);
+                    t.prm.in = single_view(eptr(slotp(D1, me), pl0 * ny * nzc + nzm, es), (long long)(ny * nzc), 0, (long long)nzc);
+                    seg_view(t.prm.out, tab_y, G2, [&](int q, int r) {
+                        const size_t nyq = g.oy.size[q];
+                        return mkseg(eptr(slotp(D2, r), nx * nyq * nzm + (x0 + pl0) * nyq * rem, es), (long long)(nyq * rem), 0, (long long)rem, g.oy.start[q]);
+                    });
+                    if (gi + 1 == NG) t.record = ev_y[c] = nev++;
+                    sc.steps.push_back(t);
+                }
             }
         }
         for (size_t c = 0; c < NSc; ++c) {
@@ -874,6 +919,14 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
             s.out_user = 2;
             s.stream = 2;
             sc.steps.push_back(s);
+            if (CH && rem && c + 1 == NSc) {
+                Step t = s;
+                t.label = "x pass (tail)";
+                t.prm.A0 = int(oy_me); t.prm.A1 = 1; t.prm.B = int(rem);
+                t.prm.in = single_view(eptr(slotp(D2, me), nx * oy_me * nzm, es), (long long)rem, 0, (long long)(oy_me * rem));
+                t.prm.out = single_view((void*)(size_t)(nzm * es), (long long)nzc, 0, (long long)(oy_me * nzc));
+                sc.steps.push_back(t);
+            }
         }
     } else {
         std::vector<int> ev_x(NS), ev_yi(NS);
@@ -1376,7 +1429,8 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         // Blocked intermediate layout for the slab's y -> x hand-over: [Nzc/CH][Nx][Ny_q][CH].  The rows a y-pass tile
         // sends to one destination are adjacent (512-byte warp stores instead of 64-byte rows: what NVLink needs),
         // and the x pass reads rows 16 KB apart instead of one row per 2 MB page (tools/layout_probe.py).
-        // Needs CH | Nzc, i.e. complex plans with power-of-two Nz.  DFFT_BLOCKED=0 disables.
+        // The Nzc % CH leftover columns (one for R2C plans: Nzc = Nz/2+1) travel in a small plain-layout tail region
+        // behind the blocked part, handled by two tiny extra launches.  DFFT_BLOCKED=0 disables.
         // NVLink store efficiency grows with the contiguous run per row: 64-byte rows reach 434 GB/s per direction,
         // 128-byte rows 700 GB/s, 2 KB runs 704 GB/s (profiles/r01_8gpu, r01_bench_n2_*): exchanging passes prefer the
         // wide tile even though it is slower as a purely local pass.  DFFT_XCHG_WIDE=0 keeps the narrow tile.
@@ -1384,7 +1438,7 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         p->xchg_tile_pref = (ew && atoi(ew) == 0) ? 1 : 2;
         const char* eb = getenv("DFFT_BLOCKED");
         const int ch = eb ? atoi(eb) : 8;
-        p->blocked_ch = (decomp == DFFT_SLAB_ZY_THEN_X && ch > 0 && g.nzc % size_t(ch) == 0 && g.nzc >= size_t(4 * ch)) ? ch : 0;
+        p->blocked_ch = (decomp == DFFT_SLAB_ZY_THEN_X && ch > 0 && g.nzc >= size_t(4 * ch)) ? ch : 0;
     }
     if (dry) {
         // fake, rank-distinct slot addresses: ((rank + 1) << 44) + slot * slot_bytes; user buffers are offsets

@@ -225,6 +225,10 @@ CASES = [
     (8, SL, dfft.R2C, (32, 16, 64), 8, 1, P2P, STREAMS),      # overlapped schedule, R2C (plain layout)
     (8, SL, dfft.C2C, (32, 16, 256), 8, 1, P2P, STREAMS),     # overlapped + blocked
     (2, SL, dfft.C2C, (8, 8, 128), 2, 1, P2P, STREAMS),
+    (4, SL, dfft.R2C, (8, 16, 128), 4, 1, P2P, SYNC),         # blocked + tail column (Nzc = 65)
+    (8, SL, dfft.R2C, (16, 8, 64), 8, 1, P2P, STREAMS),       # overlapped + blocked + tail (Nzc = 33)
+    (1, SL, dfft.R2C, (4, 8, 256), 1, 1, P2P, SYNC),
+    (3, SL, dfft.R2C, (16, 16, 64), 3, 1, P2P, STREAMS),      # uneven splits with the tail
     (4, ZY, dfft.R2C, (8, 4, 32), 4, 1, P2P, SYNC),
     (4, ZY, dfft.C2C, (8, 4, 16), 4, 1, A2A, SYNC),
     (8, PE, dfft.R2C, (8, 16, 32), 2, 4, P2P, SYNC),
