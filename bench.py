@@ -271,6 +271,21 @@ def main(argv=None):
     plan.wait()
     launches = plan.lastLaunchCount() * args.steps
     ms_step = total_ms / args.steps
+    # inverse transform of the same grid (reported beside the headline; BASELINE config 1 names forward+inverse)
+    inv_steps = max(3, min(args.steps, 10))
+    back = torch.empty_like(x)
+    if c2c:
+        inv = lambda: plan.execC2C(back, out, dfft.INVERSE, stream=stream)
+    else:
+        inv = lambda: plan.execC2R(back, out, stream=stream)
+    for _ in range(2):
+        inv()
+    plan.wait()
+    ms_inverse = timed(inv, inv_steps) / inv_steps
+    plan.wait()
+    del back
+    step()  # restore the forward result in `out`
+    plan.wait()
     fl = flops_c2c(shape) * (1.0 if c2c else 0.5)
     value = fl / (ms_step * 1e-3) / 1e9
 
@@ -414,7 +429,7 @@ def main(argv=None):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.prec, "data": "synthetic",
             "config": {"workload": f"{shape[0]}x{shape[1]}x{shape[2]} complex-{'double' if f64 else 'float'} "
                                    f"{'C2C' if c2c else 'R2C'} forward 3D FFT, {args.decomp} decomposition",
-                       "parallelism": par, "comm_method": args.comm, "send_method": send, "sequential_schedule_ms": seq_ms, "points_per_gpu": int(ntot_local),
+                       "parallelism": par, "comm_method": args.comm, "send_method": send, "sequential_schedule_ms": seq_ms, "ms_inverse": ms_inverse, "points_per_gpu": int(ntot_local),
                        "l2_policy": "inputs (>= 2 GiB per GPU) exceed the 126 MB L2; no flush needed",
                        "gflops_literal_5N3log2N_edge": (5.0 * shape[0] * shape[1] * shape[2] * math.log2(shape[0]) / (ms_step * 1e-3) / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
