@@ -250,3 +250,14 @@ def test_full_schedules(P, decomp, transform, shape, p1, p2, comm, send, inverse
 def test_pencil_partial_schedules(d, inverse, comm):
     assert run_case(8, PE, dfft.R2C, (8, 16, 32), 2, 4, comm, SYNC, inverse, d) < 1e-12
     assert run_case(4, PE, dfft.C2C, (8, 8, 16), 2, 2, comm, SYNC, inverse, d) < 1e-12
+
+
+@pytest.mark.parametrize("env", [{"DFFT_BLOCKED": "0"}, {"DFFT_BLOCKED": "16"}, {"DFFT_BLOCKED": "4"}])
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_layout_knobs(env, inverse, monkeypatch):
+    """plain hand-over layout and other block widths give the same results"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    assert run_case(4, SL, dfft.C2C, (16, 8, 64), 4, 1, P2P, SYNC, inverse, 3) < 1e-12
+    assert run_case(4, SL, dfft.R2C, (8, 16, 128), 4, 1, P2P, STREAMS, inverse, 3) < 1e-12
+    assert run_case(2, SL, dfft.R2C, (8, 8, 256), 2, 1, A2A, SYNC, inverse, 3) < 1e-12
