@@ -1425,7 +1425,7 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
     p->work_bytes = p->slot_bytes * p->nslots;
     {
         const char* e = getenv("DFFT_XCHG_CTAS");
-        p->xchg_ctas = e ? atoi(e) : 128;
+        p->xchg_ctas = e ? atoi(e) : 96;  // best of {48, 72, 96} at 8 GPUs, close to best at 2 (profiles/r01_8gpu_b)
         // Blocked intermediate layout for the slab's y -> x hand-over: [Nzc/CH][Nx][Ny_q][CH].  The rows a y-pass tile
         // sends to one destination are adjacent (512-byte warp stores instead of 64-byte rows: what NVLink needs),
         // and the x pass reads rows 16 KB apart instead of one row per 2 MB page (tools/layout_probe.py).
@@ -1437,7 +1437,14 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         const char* ew = getenv("DFFT_XCHG_WIDE");
         p->xchg_tile_pref = (ew && atoi(ew) == 0) ? 1 : 2;
         const char* eb = getenv("DFFT_BLOCKED");
-        const int ch = eb ? atoi(eb) : 8;
+        // block width = the widest tile the y and x passes use for these lengths (fft_kernels.cuh: Shape::TBT —
+        // 4096 points per tile, rows of at least 64 bytes, at most 32 columns), never below 8 elements
+        auto tile_cols = [&](size_t n) {
+            size_t w = 4096 / n, lo = precision == DFFT_F64 ? 4 : 8;
+            return w < lo ? lo : (w > 32 ? size_t(32) : w);
+        };
+        int ch = int(std::max<size_t>(8, std::max(tile_cols(ny), tile_cols(nx))));
+        if (eb) ch = atoi(eb);
         p->blocked_ch = (decomp == DFFT_SLAB_ZY_THEN_X && ch > 0 && g.nzc >= size_t(4 * ch)) ? ch : 0;
     }
     if (dry) {

@@ -261,3 +261,12 @@ def test_layout_knobs(env, inverse, monkeypatch):
     assert run_case(4, SL, dfft.C2C, (16, 8, 64), 4, 1, P2P, SYNC, inverse, 3) < 1e-12
     assert run_case(4, SL, dfft.R2C, (8, 16, 128), 4, 1, P2P, STREAMS, inverse, 3) < 1e-12
     assert run_case(2, SL, dfft.R2C, (8, 8, 256), 2, 1, A2A, SYNC, inverse, 3) < 1e-12
+
+
+@pytest.mark.parametrize("shape,P", [((128, 128, 128), 4), ((64, 256, 256), 2), ((256, 64, 128), 8), ((16, 16, 128), 1)])
+@pytest.mark.parametrize("transform", [dfft.C2C, dfft.R2C])
+def test_block_width_follows_tile_width(shape, P, transform):
+    """short lines use wider tiles (16 / 32 columns), and the hand-over block width follows them"""
+    assert run_case(P, SL, transform, shape, P, 1, P2P, SYNC, 0, 3) < 1e-12
+    if P > 1:
+        assert run_case(P, SL, transform, shape, P, 1, P2P, STREAMS, 0, 3) < 1e-12
