@@ -528,10 +528,16 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
             // rows are only adjacent when the tile is CH wide: with remote peers take the wide tile (TB = CH = 8 for
             // the 1024-point f64 pass; measured 449 -> 700 GB/s per direction), locally the faster narrow one
             s2.prm.tile_pref = G2.size() > 1 ? p->xchg_tile_pref : 1;
-            seg_view(s2.prm.out, tab_y_out, G2, [&](int q, int r) {
-                const size_t nyq = g.oy.size[q];
-                return mkseg(eptr(slotp(D2, r), x0_i * nyq * CH, es), (long long)(nyq * CH), (long long)(g.nx * nyq * CH), (long long)CH, g.oy.start[q]);
-            });
+            if (G2.size() == 1) {
+                // one rank: keep x innermost, [ny][nzm/CH][nx][CH] — every x-pass tile is one contiguous block
+                // (measured 6254 GB/s for the 512-point x pass, profiles/r01_bench_n1.json)
+                s2.prm.out = single_view(slotp(D2, me), (long long)CH, (long long)(g.nx * CH), (long long)((nzm / CH) * g.nx * CH));
+            } else {
+                seg_view(s2.prm.out, tab_y_out, G2, [&](int q, int r) {
+                    const size_t nyq = g.oy.size[q];
+                    return mkseg(eptr(slotp(D2, r), x0_i * nyq * CH, es), (long long)(nyq * CH), (long long)(g.nx * nyq * CH), (long long)CH, g.oy.start[q]);
+                });
+            }
             if (rem) {  // leftover columns z in [nzm, nzc): plain layout [nx][ny_q][rem] behind the blocked part
                 s2t = s2;
                 have_tail = true;
@@ -572,7 +578,10 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
         if (CH) {
             // in: [nzc/CH][nx][oy_i][CH]: a0 = y_loc, a1 = z chunk, n = x
             s3.prm.A0 = int(oy_i); s3.prm.A1 = int(nzm / CH); s3.prm.B = int(CH);
-            s3.prm.in = single_view(slotp(D2, me), (long long)CH, (long long)(g.nx * oy_i * CH), (long long)(oy_i * CH));
+            if (G2.size() == 1)
+                s3.prm.in = single_view(slotp(D2, me), (long long)((nzm / CH) * g.nx * CH), (long long)(g.nx * CH), (long long)CH);
+            else
+                s3.prm.in = single_view(slotp(D2, me), (long long)CH, (long long)(g.nx * oy_i * CH), (long long)(oy_i * CH));
             s3.prm.out = single_view(nullptr, (long long)nz_j, (long long)CH, (long long)(oy_i * nz_j));
             if (rem) {
                 Step s3t = s3;
