@@ -92,3 +92,22 @@ def test_job_runner_maps_reference_job_files():
     assert "-t 4" in first and "-d" in cmds[0] and "-c" not in cmds[0] and "-nx 128" in first and "-w 1" in first
     assert "-nz 256" in " ".join(cmds[1])
     assert "cli.py pencil" in " ".join(cmds[2]) and "-p1 2" in " ".join(cmds[2])
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """bench.py --impl reference (the CPU arm: oracle port, pocketfft on the host cores) prints the contract's JSON
+    line and needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--shape", "32,32,32"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "GFLOP/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    # other ranks of a torchrun launch exit without work
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, timeout=120, env=env)
+    assert r2.returncode == 0 and r2.stdout.strip() == ""
