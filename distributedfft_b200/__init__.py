@@ -5,6 +5,7 @@ from .params import (CommunicationMethod, Configurations, GlobalSize, Partition,
                      Slab_Partition, partition_sizes)
 from .host import HostExecutor
 from .mpicufft import (C2C, F32, F64, FORWARD, INVERSE, PENCIL, R2C, SLAB_Z_THEN_YX, SLAB_ZY_THEN_X, Comm, MPIcuFFT,
-                       MPIcuFFT_Pencil, MPIcuFFT_Slab, MPIcuFFT_Slab_Z_Then_YX, fft1d_contig, fft1d_general, fft1d_strided, layout)
+                       MPIcuFFT_Pencil, MPIcuFFT_Pencil_Opt1, MPIcuFFT_Slab, MPIcuFFT_Slab_Opt1, MPIcuFFT_Slab_Z_Then_YX,
+                       MPIcuFFT_Slab_Z_Then_YX_Opt1, fft1d_contig, fft1d_general, fft1d_strided, layout)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

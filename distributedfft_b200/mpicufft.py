@@ -26,6 +26,10 @@ def _ptr(buf) -> int:
     if isinstance(buf, int):
         return buf
     if hasattr(buf, "data_ptr"):
+        if hasattr(buf, "is_contiguous") and not buf.is_contiguous():
+            raise ValueError("buffers must be contiguous ([x][y][z], z fastest)")
+        if hasattr(buf, "is_cuda") and not buf.is_cuda:
+            raise ValueError("buffers must live in CUDA device memory (use HostExecutor for host buffers)")
         return int(buf.data_ptr())
     raise TypeError(f"unsupported buffer type {type(buf)}")
 
@@ -250,6 +254,14 @@ class MPIcuFFT_Pencil(MPIcuFFT):
                 d[f"size_{ax}"], d[f"start_{ax}"] = partition_sizes(n, parts)
             return d
         return dims(p.P1, p.P2, 1, g.Nz), dims(p.P1, 1, p.P2, nzc), dims(1, p.P1, p.P2, nzc)
+
+
+# "Realigned" (Opt1) classes of the reference — include/mpicufft_slab_opt1.hpp, mpicufft_slab_z_then_yx_opt1.hpp,
+# mpicufft_pencil_opt1.hpp: same results and output layouts as the default classes; the transposing store they add is
+# always fused into the FFT passes here, so they are aliases.
+MPIcuFFT_Slab_Opt1 = MPIcuFFT_Slab
+MPIcuFFT_Slab_Z_Then_YX_Opt1 = MPIcuFFT_Slab_Z_Then_YX
+MPIcuFFT_Pencil_Opt1 = MPIcuFFT_Pencil
 
 
 def layout(decomp: int, transform: int, nx: int, ny: int, nz: int, p1: int, p2: int, rank: int, which: int):

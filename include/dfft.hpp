@@ -166,3 +166,11 @@ private:
     GlobalSize gs_{1, 1, 2};
     Partition part_{1, 1};
 };
+
+// "Realigned" variants (/root/reference/include/mpicufft_slab_opt1.hpp, mpicufft_slab_z_then_yx_opt1.hpp,
+// mpicufft_pencil_opt1.hpp): in the reference they make cuFFT store transposed so that the send side is contiguous;
+// results and output layouts are identical to the default classes.  Here the transposing store is always fused into
+// the FFT passes, so the names are aliases.
+template <typename T> using MPIcuFFT_Slab_Opt1 = MPIcuFFT_Slab<T>;
+template <typename T> using MPIcuFFT_Slab_Z_Then_YX_Opt1 = MPIcuFFT_Slab_Z_Then_YX<T>;
+template <typename T> using MPIcuFFT_Pencil_Opt1 = MPIcuFFT_Pencil<T>;
