@@ -111,3 +111,14 @@ def test_bench_reference_arm_runs_on_cpu():
     r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                         capture_output=True, text=True, timeout=120, env=env)
     assert r2.returncode == 0 and r2.stdout.strip() == ""
+
+
+def test_cpp_shim_header_compiles():
+    """include/dfft.hpp (the reference's class names over the C ABI) is valid C++17 on its own."""
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "t.cpp")
+        open(src, "w").write('#include "dfft.hpp"\nint main() { GlobalSize g(8, 8, 8); Pencil_Partition p(2, 4); '
+                             'MPIcuFFT_Slab_Opt1<double>* a = nullptr; MPIcuFFT_Pencil_Opt1<float>* b = nullptr; (void)a; (void)b; return int(g.Nz_out + p.P2) == 9 ? 0 : 1; }\n')
+        subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), src], check=True)
