@@ -236,3 +236,22 @@ def test_host_executor_pipeline():
     hb.wait()
     assert O.rel_l2(back.numpy().reshape(shape), ins[2] * np.prod(shape)) < 1e-10
     plan.destroy()
+
+
+def test_caller_supplied_work_area():
+    """initFFT(.., allocate=false) + setWorkArea(device) — mpicufft_slab.cpp:236-281: the caller owns the arena."""
+    shape = (32, 32, 64)
+    plan = dfft.MPIcuFFT_Slab(dfft.Configurations(), dfft.Comm(), precision="double", transform="r2c")
+    plan.initFFT(dfft.GlobalSize(*shape), None, False)
+    x = dev(O.real_input(shape))
+    out = torch.empty((32, 32, 33), dtype=torch.complex128, device="cuda")
+    from distributedfft_b200._lib import DfftError
+    with pytest.raises(DfftError):
+        plan.execR2C(out, x)  # no work area yet
+    arena = torch.empty(plan.getWorkSizeDevice(), dtype=torch.uint8, device="cuda")
+    plan.setWorkArea(arena)
+    assert plan.getWorkAreaDevice() == arena.data_ptr()
+    plan.execR2C(out, x)
+    assert O.rel_l2(host(out), O.fft_r2c(host(x))) < 1e-10
+    plan.destroy()
+    assert arena.numel() > 0  # still ours
