@@ -183,6 +183,8 @@ struct CtaFft {
     static constexpr size_t TILE_BYTES = size_t(L::ELEMS) * sizeof(cx<T>);
     static constexpr size_t TABLE_BYTES = size_t(2) * LINES * MAXSEG * sizeof(unsigned long long);
     static constexpr size_t SMEM_BYTES = TILE_BYTES + TABLE_BYTES;
+    static_assert(THREADS >= 1 && THREADS <= 1024, "CTA size out of range");
+    static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit the 227 KB of shared memory a CTA can use on sm_100a");
 
     static __device__ __forceinline__ int sidx(int n, int t) { return L::idx(n, t); }
 
