@@ -122,3 +122,40 @@ def test_cpp_shim_header_compiles():
         open(src, "w").write('#include "dfft.hpp"\nint main() { GlobalSize g(8, 8, 8); Pencil_Partition p(2, 4); '
                              'MPIcuFFT_Slab_Opt1<double>* a = nullptr; MPIcuFFT_Pencil_Opt1<float>* b = nullptr; (void)a; (void)b; return int(g.Nz_out + p.P2) == 9 ? 0 : 1; }\n')
         subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), src], check=True)
+
+
+def _dry_plan(P, rank, decomp, transform, shape, p1=0, p2=1):
+    comm = C.c_void_p()
+    _lib.check(_lib.lib().dfft_comm_create_dry(rank, P, C.byref(comm)))
+    plan = C.c_void_p()
+    rc = _lib.lib().dfft_plan_create(comm, None, decomp, dfft.F64, transform, shape[0], shape[1], shape[2], p1 or P, p2, 1, C.byref(plan))
+    msg = (_lib.lib().dfft_last_error_string() or b"").decode()
+    if rc == 0:
+        _lib.lib().dfft_plan_destroy(plan)
+    _lib.lib().dfft_comm_destroy(comm)
+    return rc, msg
+
+
+def test_plan_argument_validation_without_gpu():
+    """initFFT-time checks through geometry-only plans: unsupported lengths, empty shares, bad grids."""
+    assert _dry_plan(1, 0, dfft.SLAB_ZY_THEN_X, dfft.R2C, (64, 64, 64))[0] == 0
+    rc, msg = _dry_plan(1, 0, dfft.SLAB_ZY_THEN_X, dfft.R2C, (96, 64, 64))
+    assert rc == -5 and "powers of two" in msg                      # DFFT_ERR_UNSUPPORTED
+    rc, msg = _dry_plan(1, 0, dfft.SLAB_ZY_THEN_X, dfft.R2C, (64, 64, 2))
+    assert rc == -5                                                 # R2C needs Nz >= 4
+    assert _dry_plan(1, 0, dfft.SLAB_ZY_THEN_X, dfft.C2C, (64, 64, 2))[0] == 0
+    rc, msg = _dry_plan(8, 3, dfft.SLAB_ZY_THEN_X, dfft.R2C, (4, 64, 64))
+    assert rc == -1 and "without data" in msg                       # more ranks than x planes
+    rc, msg = _dry_plan(8, 0, dfft.PENCIL, dfft.R2C, (64, 64, 64), p1=3, p2=2)
+    assert rc == -1 and "P1*P2" in msg
+    assert _dry_plan(8, 7, dfft.PENCIL, dfft.R2C, (64, 64, 64), p1=2, p2=4)[0] == 0
+    rc, msg = _dry_plan(16, 0, dfft.SLAB_ZY_THEN_X, dfft.R2C, (16384, 64, 64))
+    assert rc == -5                                                 # lengths above 8192
+    # geometry-only plans refuse to execute
+    comm = C.c_void_p()
+    _lib.check(_lib.lib().dfft_comm_create_dry(0, 1, C.byref(comm)))
+    plan = C.c_void_p()
+    _lib.check(_lib.lib().dfft_plan_create(comm, None, dfft.SLAB_ZY_THEN_X, dfft.F64, dfft.R2C, 8, 8, 8, 1, 1, 1, C.byref(plan)))
+    assert _lib.lib().dfft_exec_r2c(plan, C.c_void_p(16), C.c_void_p(16)) == -4
+    _lib.lib().dfft_plan_destroy(plan)
+    _lib.lib().dfft_comm_destroy(comm)
