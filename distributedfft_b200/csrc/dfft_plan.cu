@@ -290,6 +290,8 @@ namespace dfft {
 
 static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc);
 static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc);
+static int build_overlapped_pencil(dfft_plan_s* p, Schedule& sc);
+static bool pencil_overlap_enabled();
 
 }  // namespace dfft
 
@@ -993,6 +995,152 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
 
 }  // namespace dfft
 
+namespace dfft {
+
+static bool pencil_overlap_enabled() {
+    const char* e = getenv("DFFT_PENCIL_OVERLAP");
+    return e && atoi(e) != 0;
+}
+
+// Overlapped pencil schedule, forward, Peer2Peer on both transpositions (EXPERIMENTAL: enabled with
+// DFFT_PENCIL_OVERLAP=1 + send_method Streams; addressing and ordering are covered by the CPU schedule emulation,
+// GPU timing is still to be measured).
+//   stream 0: z pass per plane group, scattering along z into the row peers' slot A            (NVLink-bound)
+//   stream 1: per plane group: meet the row peers; then the y pass per (plane group, z chunk), persistent on
+//             `xchg_ctas` CTAs, scattering along y into the column peers' slot B                 (NVLink-bound)
+//   stream 2: per z chunk: meet the column peers, x pass of that chunk                           (HBM-bound)
+// Only the x pass can hide behind an exchange (both scatters share the NVLink ports).
+static int build_overlapped_pencil(dfft_plan_s* p, Schedule& sc) {
+    const Geometry& g = p->g;
+    const int me = p->rank;
+    const int pi = g.pi(me), pj = g.pj(me);
+    const size_t es = p->esize;
+    const bool c2c = g.transform == DFFT_C2C;
+    Tables& T = p->tabs;
+    sc.steps.clear();
+    sc.overlapped = true;
+    const size_t ny = g.ny, nx = g.nx;
+    const size_t nx_i = g.sx.size[pi], x0_i = g.sx.start[pi];
+    const size_t ny_j = g.sy.size[pj], y0_j = g.sy.start[pj];
+    const size_t nz_j = g.sz.size[pj];
+    const size_t oy_i = g.oy.size[pi];
+    const std::vector<int>& G1 = p->grp[1];
+    const std::vector<int>& G2 = p->grp[2];
+    const int D1 = 0, D2 = 1;
+    auto slotp = [&](int s_, int r) -> void* { return p->slot_ptr[s_][r]; };
+    int nev = 0;
+
+    auto new_pass = [&](PassKind kind, size_t n, const char* label, Step& s) -> int {
+        s = Step();
+        s.type = STEP_PASS;
+        s.kind = kind;
+        s.label = label;
+        s.log2n = ilog2_exact(n);
+        if (s.log2n < 1 || s.log2n > MAX_LOG2N) return fail(DFFT_ERR_UNSUPPORTED, "unsupported axis length");
+        s.prm.A0 = 1; s.prm.A1 = 1; s.prm.B = 1;
+        s.prm.inverse = 0;
+        void* tw = nullptr;
+        if (T.get_tw(s.log2n, &tw) != cudaSuccess) return fail(DFFT_ERR_CUDA, "twiddle table allocation failed");
+        s.prm.tw = tw;
+        if (kind == PASS_R2C) {
+            void* tw2 = nullptr;
+            if (T.get_tw2(s.log2n, &tw2) != cudaSuccess) return fail(DFFT_ERR_CUDA, "twiddle table allocation failed");
+            s.prm.tw2 = tw2;
+        }
+        return DFFT_SUCCESS;
+    };
+    auto rendezvous = [&](int group, int stream) {
+        Step s;
+        s.type = STEP_RENDEZVOUS;
+        s.label = group == 0 ? "entry rendezvous" : (group == 1 ? "rendezvous 1" : "rendezvous 2");
+        s.group = group;
+        s.phase_id = group;
+        s.stream = stream;
+        return s;
+    };
+
+    // every rank must build the same number of steps: derive the group / chunk counts from global minima
+    size_t min_nx = nx, min_nz = g.nzc;
+    for (size_t v : g.sx.size) min_nx = std::min(min_nx, v);
+    for (size_t v : g.sz.size) min_nz = std::min(min_nz, v);
+    const size_t NG = std::min<size_t>(4, min_nx);
+    const size_t NS = min_nz >= 128 ? 4 : (min_nz >= 32 ? 2 : 1);
+    Split groups, chunks;
+    groups.make(nx_i, NG);
+    chunks.make(nz_j, NS);
+    const unsigned char *tab_z = nullptr, *tab_y = nullptr;
+    if (T.seg_table(g.sz, &tab_z) != cudaSuccess || T.seg_table(g.oy, &tab_y) != cudaSuccess) return fail(DFFT_ERR_CUDA, "segment table");
+
+    sc.steps.push_back(rendezvous(0, 0));
+    const int ev_entry = nev++;
+    sc.steps.back().record = ev_entry;
+    int rc;
+    std::vector<int> ev_z(NG), ev_y(NS);
+    for (size_t gi = 0; gi < NG; ++gi) {
+        Step s;
+        rc = new_pass(c2c ? PASS_C2C_CONTIG : PASS_R2C, c2c ? g.nz : g.nz / 2, c2c ? "z pass" : "z pass (R2C)", s);
+        if (rc) return rc;
+        const size_t pl0 = groups.start[gi], npl = groups.size[gi];
+        const long long pitch = c2c ? (long long)g.nz : (long long)(g.nz / 2);
+        s.prm.A0 = int(npl); s.prm.A1 = int(ny_j);
+        s.prm.in = single_view((void*)(size_t)(pl0 * ny_j * pitch * es), pitch * (long long)ny_j, pitch, 1);
+        s.in_user = 1;
+        seg_view(s.prm.out, tab_z, G1, [&](int q, int r) {
+            const size_t nzq = g.sz.size[q];
+            return mkseg(eptr(slotp(D1, r), (pl0 * ny + y0_j) * nzq, es), (long long)(ny * nzq), (long long)nzq, 1, g.sz.start[q]);
+        });
+        s.stream = 0;
+        s.record = ev_z[gi] = nev++;
+        sc.steps.push_back(s);
+    }
+    for (size_t c = 0; c < NS; ++c) {
+        const size_t z0 = chunks.start[c], zc = chunks.size[c];
+        for (size_t gi = 0; gi < NG; ++gi) {
+            const size_t pl0 = groups.start[gi], npl = groups.size[gi];
+            if (c == 0) {
+                Step r = rendezvous(1, 1);  // all row peers have delivered plane group gi
+                r.waits.push_back(ev_z[gi]);
+                if (gi == 0) r.waits.push_back(ev_entry);
+                sc.steps.push_back(r);
+            }
+            Step s;
+            rc = new_pass(PASS_C2C_TILED, ny, "y pass", s);
+            if (rc) return rc;
+            s.prm.A0 = int(npl); s.prm.A1 = 1; s.prm.B = int(zc);
+            s.prm.in = single_view(eptr(slotp(D1, me), pl0 * ny * nz_j + z0, es), (long long)(ny * nz_j), 0, (long long)nz_j);
+            seg_view(s.prm.out, tab_y, G2, [&](int q, int r) {
+                const size_t nyq = g.oy.size[q];
+                return mkseg(eptr(slotp(D2, r), (x0_i + pl0) * nyq * nz_j + z0, es), (long long)(nyq * nz_j), 0, (long long)nz_j, g.oy.start[q]);
+            });
+            s.prm.max_ctas = p->xchg_ctas;
+            s.prm.tile_pref = G2.size() > 1 ? p->xchg_tile_pref : 0;
+            s.stream = 1;
+            if (gi + 1 == NG) s.record = ev_y[c] = nev++;
+            sc.steps.push_back(s);
+        }
+    }
+    for (size_t c = 0; c < NS; ++c) {
+        const size_t z0 = chunks.start[c], zc = chunks.size[c];
+        Step r = rendezvous(2, 2);
+        r.waits.push_back(ev_y[c]);
+        sc.steps.push_back(r);
+        Step s;
+        rc = new_pass(PASS_C2C_TILED, nx, "x pass", s);
+        if (rc) return rc;
+        s.prm.A0 = 1; s.prm.A1 = int(oy_i); s.prm.B = int(zc);
+        s.prm.in = single_view(eptr(slotp(D2, me), z0, es), 0, (long long)nz_j, (long long)(oy_i * nz_j));
+        s.prm.out = single_view((void*)(size_t)(z0 * es), 0, (long long)nz_j, (long long)(oy_i * nz_j));
+        s.out_user = 2;
+        s.stream = 2;
+        sc.steps.push_back(s);
+    }
+    sc.nevents = nev;
+    sc.built = true;
+    return DFFT_SUCCESS;
+}
+
+}  // namespace dfft
+
 // =====================================================================================================
 // memory / peer mapping
 // =====================================================================================================
@@ -1212,7 +1360,10 @@ static int exec_common(dfft_plan_t p, void* out, const void* in, int inverse, in
         int rc = DFFT_SUCCESS;
         const bool want_overlap = p->cfg.send_method == DFFT_SEND_STREAMS && d == 3 && p->P > 1 && p->g.decomp == DFFT_SLAB_ZY_THEN_X &&
                                   p->direct2 && p->xchg_ctas >= 0;
+        const bool want_pencil_overlap = p->cfg.send_method == DFFT_SEND_STREAMS && d == 3 && !inverse && p->g.decomp == DFFT_PENCIL &&
+                                         p->direct1 && p->direct2 && p->grp[1].size() > 1 && p->grp[2].size() > 1 && pencil_overlap_enabled();
         if (want_overlap) rc = build_overlapped_slab(p, inverse ? 1 : 0, sc);
+        else if (want_pencil_overlap) rc = build_overlapped_pencil(p, sc);
         else rc = build_schedule(p, inverse ? 1 : 0, d, sc);
         if (rc) return rc;
         if (g_view_error) return fail(DFFT_ERR_STATE, "internal: segments of one view disagree on the axis stride");
@@ -1698,7 +1849,10 @@ int dfft_plan_describe(dfft_plan_t p, int inverse, int d, char* buf, size_t capa
     if (!sc.built) {
         g_view_error = false;
         const bool want_overlap = p->cfg.send_method == DFFT_SEND_STREAMS && d == 3 && p->P > 1 && p->g.decomp == DFFT_SLAB_ZY_THEN_X && p->direct2;
-        int rc = want_overlap ? build_overlapped_slab(p, inverse ? 1 : 0, sc) : build_schedule(p, inverse ? 1 : 0, d, sc);
+        const bool want_pencil_overlap = p->cfg.send_method == DFFT_SEND_STREAMS && d == 3 && !inverse && p->g.decomp == DFFT_PENCIL &&
+                                         p->direct1 && p->direct2 && p->grp[1].size() > 1 && p->grp[2].size() > 1 && pencil_overlap_enabled();
+        int rc = want_overlap ? build_overlapped_slab(p, inverse ? 1 : 0, sc)
+                              : (want_pencil_overlap ? build_overlapped_pencil(p, sc) : build_schedule(p, inverse ? 1 : 0, d, sc));
         if (rc) return rc;
         if (g_view_error) return fail(DFFT_ERR_STATE, "internal: segments of one view disagree on the axis stride");
     }

@@ -270,3 +270,18 @@ def test_block_width_follows_tile_width(shape, P, transform):
     assert run_case(P, SL, transform, shape, P, 1, P2P, SYNC, 0, 3) < 1e-12
     if P > 1:
         assert run_case(P, SL, transform, shape, P, 1, P2P, STREAMS, 0, 3) < 1e-12
+
+
+@pytest.mark.parametrize("P,shape,p1,p2,transform", [
+    (8, (16, 32, 256), 2, 4, dfft.C2C), (8, (32, 16, 64), 4, 2, dfft.R2C), (4, (8, 8, 128), 2, 2, dfft.C2C),
+    (8, (16, 16, 1024), 2, 4, dfft.R2C)])
+def test_overlapped_pencil_schedule(P, shape, p1, p2, transform, monkeypatch):
+    """experimental overlapped pencil schedule (DFFT_PENCIL_OVERLAP=1, SendMethod Streams), forward"""
+    monkeypatch.setenv("DFFT_PENCIL_OVERLAP", "1")
+    assert run_case(P, PE, transform, shape, p1, p2, P2P, STREAMS, 0, 3) < 1e-12
+    sched = describe(0, P, PE, transform, shape, p1, p2, P2P, STREAMS, 0, 3)
+    assert sched["overlapped"] and {s["stream"] for s in sched["steps"]} == {0, 1, 2}
+    # the inverse and the default (env unset) stay on the sequential schedule
+    assert run_case(P, PE, transform, shape, p1, p2, P2P, STREAMS, 1, 3) < 1e-12
+    monkeypatch.delenv("DFFT_PENCIL_OVERLAP")
+    assert not describe(0, P, PE, transform, shape, p1, p2, P2P, STREAMS, 0, 3)["overlapped"]
