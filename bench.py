@@ -368,11 +368,28 @@ def main(argv=None):
             roofline["nvlink"] = link(cplx_bytes * (world - 1) / world, t_x,
                                       "Peer2Peer: the scattering pass stores straight into the peers' slots, so its duration is the transfer time")
 
+    cpu = None
+    cufft_ms = None
+    if rank == 0 and world == 1:
+        if not args.no_cpu:
+            cs = bounded_cpu_shape(shape)
+            sec, cores, desc = cpu_fft_sample(cs, reps=1)
+            cpu = {"value": flops_c2c(cs) / sec / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": desc, "ms": sec * 1e3}
+        ref = os.path.join(ROOT, "oracle", "_ref", "libcufft_ref.so")
+        if os.path.exists(ref) and c2c:
+            try:
+                lib = C.CDLL(ref)
+                lib.cufft_ref_3d.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int]
+                msf = C.c_float()
+                if lib.cufft_ref_3d(1 if f64 else 0, 0, shape[0], shape[1], shape[2], out.data_ptr(), x.data_ptr(), C.byref(msf), 10) == 0:
+                    cufft_ms = float(msf.value)
+            except Exception:
+                cufft_ms = None
+
     # end-to-end through the public host-buffer API (HostExecutor): every step copies its input block from pinned
     # host memory, transforms it and copies the spectrum block back; consecutive steps are pipelined (the D2H of
     # step i overlaps the H2D of step i+1), all inside the timed region
-    e2e = None
-    if not args.no_e2e:
+    def run_e2e():
         hin = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
         hin.copy_(x)
         n_out = osz[0] * osz[1] * osz[2]
@@ -398,32 +415,12 @@ def main(argv=None):
         t = float(tms.item()) / ksteps
         # sanity: the spectrum that arrived on the host is the device result
         chk = float((hout[:1024].cuda() - hx.d_out[(hx.count - 1) & 1][:1024]).abs().max())
-        e2e = {"value": fl / (t * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": t, "wall_ms_per_step": wall_ms / ksteps,
-               "h2d_bytes_per_step": int(x.numel() * x.element_size() * world), "d2h_bytes_per_step": int(n_out * es * world),
-               "pipeline": "H2D(i+1) overlaps D2H(i); 2 device buffer sets", "host_equals_device": chk == 0.0}
-        del hin, hout, hx
+        return {"value": fl / (t * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": t, "wall_ms_per_step": wall_ms / ksteps,
+                "h2d_bytes_per_step": int(x.numel() * x.element_size() * world), "d2h_bytes_per_step": int(n_out * es * world),
+                "pipeline": "H2D(i+1) overlaps D2H(i); 2 device buffer sets", "host_equals_device": chk == 0.0}
 
-    clocks = sampler.stop() if sampler else None
-    cpu = None
-    cufft_ms = None
-    if rank == 0 and world == 1:
-        if not args.no_cpu:
-            cs = bounded_cpu_shape(shape)
-            sec, cores, desc = cpu_fft_sample(cs, reps=1)
-            cpu = {"value": flops_c2c(cs) / sec / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": desc, "ms": sec * 1e3}
-        ref = os.path.join(ROOT, "oracle", "_ref", "libcufft_ref.so")
-        if os.path.exists(ref) and c2c:
-            try:
-                lib = C.CDLL(ref)
-                lib.cufft_ref_3d.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int]
-                msf = C.c_float()
-                if lib.cufft_ref_3d(1 if f64 else 0, 0, shape[0], shape[1], shape[2], out.data_ptr(), x.data_ptr(), C.byref(msf), 10) == 0:
-                    cufft_ms = float(msf.value)
-            except Exception:
-                cufft_ms = None
-
-    if rank == 0:
-        line = {
+    def make_line(e2e, clocks):
+        return {
             "metric": "3D FFT GFLOP/s (5*Ntot*log2(Ntot)/t, complex-double forward)" if c2c else "3D FFT GFLOP/s (2.5*Ntot*log2(Ntot)/t, R2C forward)",
             "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.prec, "data": "synthetic",
@@ -435,7 +432,31 @@ def main(argv=None):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "cufft_1gpu_ms": cufft_ms,
         }
-        print(json.dumps(line), flush=True)
+
+    # The e2e leg runs last and is guarded: should it fail or stall on some rank, the measured line is still printed.
+    e2e = None
+    if not args.no_e2e:
+        import threading
+        finished = threading.Event()
+
+        def watchdog():
+            if not finished.wait(240):
+                if rank == 0:
+                    print(json.dumps(make_line({"error": "e2e leg did not finish within 240 s"}, sampler.stop() if sampler else None)), flush=True)
+                os._exit(0)
+
+        threading.Thread(target=watchdog, daemon=True).start()
+        try:
+            e2e = run_e2e()
+        except Exception as ex:  # report, do not lose the device-resident measurement
+            finished.set()
+            if rank == 0:
+                print(json.dumps(make_line({"error": repr(ex)[:300]}, sampler.stop() if sampler else None)), flush=True)
+            os._exit(0)
+        finished.set()
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        print(json.dumps(make_line(e2e, clocks)), flush=True)
     plan.destroy()
     comm.destroy()
     del x, out
