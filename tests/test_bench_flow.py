@@ -78,8 +78,13 @@ def _fake_dfft():
     return m
 
 
-@pytest.mark.parametrize("extra", [[], ["--transform", "r2c"], ["--no-e2e", "--no-cpu"]])
+@pytest.mark.parametrize("extra", [[], ["--transform", "r2c"], ["--no-e2e", "--no-cpu"], ["WORLD=8"], ["WORLD=8", "--decomp", "pencil", "--p1", "2", "--p2", "4", "--prec", "f32"],
+                                   ["WORLD=2", "--comm", "All2All", "--send", "Sync"]])
 def test_bench_single_gpu_flow_with_mocks(monkeypatch, capsys, extra):
+    extra = list(extra)
+    world = 1
+    if extra and extra[0].startswith("WORLD="):
+        world = int(extra.pop(0).split("=")[1])
     monkeypatch.setitem(sys.modules, "distributedfft_b200", _fake_dfft())
     monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
@@ -99,18 +104,38 @@ def test_bench_single_gpu_flow_with_mocks(monkeypatch, capsys, extra):
     monkeypatch.setattr(torch.Tensor, "data_ptr", lambda self: 0)
     monkeypatch.delenv("WORLD_SIZE", raising=False)
     monkeypatch.delenv("RANK", raising=False)
+    if world > 1:  # one rank of a torchrun launch, torch.distributed mocked
+        import torch.distributed as dist
+        monkeypatch.setenv("WORLD_SIZE", str(world)); monkeypatch.setenv("RANK", "0"); monkeypatch.setenv("LOCAL_RANK", "0")
+        monkeypatch.setattr(dist, "is_initialized", lambda: True)
+        monkeypatch.setattr(dist, "barrier", lambda *a, **k: None)
+        monkeypatch.setattr(dist, "all_reduce", lambda *a, **k: None)
     sys.path.insert(0, ROOT)
     import importlib
     bench = importlib.import_module("bench")
     monkeypatch.setattr(bench, "ClockSampler", lambda idx: types.SimpleNamespace(stop=lambda: {"sm_mhz": 1900.0, "sm_max_mhz": 1965.0, "reasons": []}))
     monkeypatch.setattr(bench, "cpu_fft_sample", lambda shape, reps=1: (0.5, 8, "mock sample"))
     monkeypatch.setattr(os.path, "exists", lambda p, _e=os.path.exists: False if p.endswith("libcufft_ref.so") else _e(p))
-    bench.main(["--steps", "4", "--warmup", "3", "--shape", "32,32,32", *extra])
+    if world > 1:
+        # per-step labels of a multi-rank slab / pencil plan
+        steps = [("entry rendezvous", 0.02), ("z pass", 0.6), ("y pass", 2.7), ("rendezvous 2", 0.01), ("x pass", 0.9)]
+        if "All2All" in extra:
+            steps = [("z pass", 0.6), ("y pass", 1.0), ("nccl all-to-all", 3.2), ("x pass", 0.9)]
+        monkeypatch.setattr(sys.modules["distributedfft_b200"].MPIcuFFT_Slab, "stepTimes", lambda self: steps)
+        monkeypatch.setattr(sys.modules["distributedfft_b200"].MPIcuFFT_Slab, "lastBreakdown", lambda self: {"fft_ms": 4.2, "exchange_ms": 0.03, "total_ms": 4.3})
+    bench.main(["--gpus", str(world), "--steps", "4", "--warmup", "3", "--shape", "32,32,32", *extra])
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
                 "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert key in line, key
-    assert line["n_gpus"] == 1 and line["gpu_launches"] == 12 and line["config"]["workload"].startswith("32x32x32")
+    assert line["n_gpus"] == world and line["gpu_launches"] == 12 and line["config"]["workload"].startswith("32x32x32")
+    if world > 1:
+        nv = line["roofline"]["nvlink"]
+        nv = nv if isinstance(nv, list) else [nv]
+        assert all(x["gbs_per_direction"] and x["gbs_per_direction"] > 0 for x in nv)
+        assert len(nv) == (2 if "pencil" in extra else 1)
+        assert line["cpu_baseline"] is None and line["config"]["send_method"] == ("Sync" if "Sync" in extra else "Streams")
+        return
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert key in line["roofline"]
     if "--no-e2e" not in extra:
