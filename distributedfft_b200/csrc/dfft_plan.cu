@@ -246,6 +246,7 @@ struct dfft_plan_s {
     int xchg_ctas = 0;                            // SMs given to the exchange pass in overlapped schedules
     int blocked_ch = 0;                           // > 0: slab forward keeps the y->x intermediate as [b/CH][Nx][CH]
     int xchg_tile_pref = 2;                       // tile preference of passes that store into other GPUs (2 = wide rows)
+    int bulk_store = 0;                           // experimental: exchanging y pass stores with cp.async.bulk (DFFT_BULK_STORE=1)
     cudaStream_t own_stream = nullptr, last_stream = nullptr;  // last_stream: stream of the last exec
     Tables tabs;
     // schedules: [fwd/inv][d-1]
@@ -530,6 +531,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
             // rows are only adjacent when the tile is CH wide: with remote peers take the wide tile (TB = CH = 8 for
             // the 1024-point f64 pass; measured 449 -> 700 GB/s per direction), locally the faster narrow one
             s2.prm.tile_pref = G2.size() > 1 ? p->xchg_tile_pref : 1;
+            s2.prm.bulk_out = G2.size() > 1 ? p->bulk_store : 0;
             if (G2.size() == 1) {
                 // one rank: keep x innermost, [ny][nzm/CH][nx][CH] — every x-pass tile is one contiguous block
                 // (measured 6254 GB/s for the 512-point x pass, profiles/r01_bench_n1.json)
@@ -544,6 +546,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
                 s2t = s2;
                 have_tail = true;
                 s2t.label = "y pass (tail)";
+                s2t.prm.bulk_out = 0;
                 s2t.phase = nullptr;
                 s2t.prm.A1 = 1; s2t.prm.B = int(rem);
                 s2t.prm.in.seg[0].base = eptr(s2.prm.in.seg[0].base, nzm, es);
@@ -872,6 +875,7 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
                     s.prm.A0 = int(npl); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
                     s.prm.in = single_view(eptr(slotp(D1, me), pl0 * ny * nzc + z0, es), (long long)(ny * nzc), (long long)CH, (long long)nzc);
                     s.prm.tile_pref = p->xchg_tile_pref;
+                    s.prm.bulk_out = p->bulk_store;
                     seg_view(s.prm.out, tab_y, G2, [&](int q, int r) {
                         const size_t nyq = g.oy.size[q];
                         return mkseg(eptr(slotp(D2, r), ((z0 / CH) * nx + x0 + pl0) * nyq * CH, es), (long long)(nyq * CH), (long long)(nx * nyq * CH),
@@ -896,6 +900,7 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
                 if (tail_here) {
                     Step t = s;
                     t.label = "y pass (tail)";
+                    t.prm.bulk_out = 0;
                     t.waits.clear();
                     t.record = -1;
                     t.prm.A0 = int(npl); t.prm.A1 = 1; t.prm.B = int(rem);
@@ -1594,6 +1599,8 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         // NVLink store efficiency grows with the contiguous run per row: 64-byte rows reach 434 GB/s per direction,
         // 128-byte rows 700 GB/s, 2 KB runs 704 GB/s (profiles/r01_8gpu, r01_bench_n2_*): exchanging passes prefer the
         // wide tile even though it is slower as a purely local pass.  DFFT_XCHG_WIDE=0 keeps the narrow tile.
+        const char* ebs = getenv("DFFT_BULK_STORE");
+        p->bulk_store = (ebs && atoi(ebs) != 0) ? 1 : 0;
         const char* ew = getenv("DFFT_XCHG_WIDE");
         p->xchg_tile_pref = (ew && atoi(ew) == 0) ? 1 : 2;
         const char* eb = getenv("DFFT_BLOCKED");

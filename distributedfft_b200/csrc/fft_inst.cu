@@ -50,6 +50,19 @@ static cudaError_t launch_tiled(const FftParams& p, cudaStream_t stream, long lo
     if (p.B <= 0) return cudaSuccess;
     const long long grid = lines * ((p.B + TB - 1) / TB);
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    if constexpr (!C::L::PAD) {
+        // experimental TMA bulk-store variant (see fft_c2c_bulk_kernel): only when the launcher's contract holds
+        if (p.bulk_out && p.in.nseg == 1 && p.out.sN == TB && p.B == TB) {
+            auto bf = fft_c2c_bulk_kernel<T, LOG2N, LOG2E, TB, false>;
+            auto bi = fft_c2c_bulk_kernel<T, LOG2N, LOG2E, TB, true>;
+            static cudaError_t onceb = set_smem(bf, C::SMEM_BYTES) != cudaSuccess ? cudaErrorInvalidValue : set_smem(bi, C::SMEM_BYTES);
+            if (onceb != cudaSuccess) return onceb;
+            const unsigned gb = unsigned((p.max_ctas > 0 && grid > p.max_ctas) ? p.max_ctas : grid);
+            if (p.inverse) bi<<<gb, C::THREADS, C::SMEM_BYTES, stream>>>(p);
+            else bf<<<gb, C::THREADS, C::SMEM_BYTES, stream>>>(p);
+            return cudaGetLastError();
+        }
+    }
     if constexpr (C::THREADS <= (sizeof(T) == 8 ? 256 : 512)) {
         if (pipe_mode() && p.max_ctas <= 0) {
             auto pf = fft_c2c_pipe_kernel<T, LOG2N, LOG2E, TB, true, false>;
