@@ -203,19 +203,6 @@ def test_cli_testcases(argv, capsys):
     assert "Result" in out or "Run complete" in out
 
 
-def test_cpp_shim_caller(tmp_path):
-    """Reference-shaped C++ caller over include/dfft.hpp (MPIcuFFT_Slab<double> etc.): round trip + Laplacian."""
-    import subprocess
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = str(tmp_path / "slab_shim_test")
-    libdir = os.path.join(root, "distributedfft_b200")
-    subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(root, "include"), "-I/usr/local/cuda/include",
-                    os.path.join(root, "tests", "cpp", "slab_shim_test.cpp"), "-o", exe, "-L" + libdir, "-ldfft",
-                    "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + libdir], check=True)
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
-
-
 def test_host_executor_pipeline():
     """HostExecutor: pinned host in -> device -> transform -> pinned host out, pipelined over submits."""
     shape = (32, 64, 128)
@@ -276,3 +263,16 @@ def test_against_committed_golden_vectors(name):
     planc.execC2C(outc, dev(O.complex_input(shape, seed=1234)), dfft.FORWARD)
     assert O.rel_l2(host(outc), g[f"{name}_c2c"]) < 1e-10
     planc.destroy()
+
+
+def test_cpp_shim_caller(tmp_path):
+    """Reference-shaped C++ caller over include/dfft.hpp (MPIcuFFT_Slab<double> etc.): round trip + Laplacian."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "slab_shim_test")
+    libdir = os.path.join(root, "distributedfft_b200")
+    subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(root, "include"), "-I/usr/local/cuda/include",
+                    os.path.join(root, "tests", "cpp", "slab_shim_test.cpp"), "-o", exe, "-L" + libdir, "-ldfft",
+                    "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
