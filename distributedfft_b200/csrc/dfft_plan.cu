@@ -132,6 +132,12 @@ struct Tables {
         *out = (const unsigned char*)d;
         return e;
     }
+    // segment tables belong to the schedules: dropped whenever the schedules are rebuilt (dfft_set_work_area)
+    void release_seg_tables() {
+        for (void* p : bytes) cudaFree(p);
+        for (auto* v : dry_store) delete v;
+        bytes.clear(); dry_store.clear(); host_tabs.clear();
+    }
     void release() {
         for (auto& kv : tw) cudaFree(kv.second);
         for (auto& kv : tw2) cudaFree(kv.second);
@@ -145,6 +151,12 @@ struct Tables {
 // flags layout (uint64): [phase][rank], NPHASE phases.  Thread i handles group member i: publishes my
 // epoch in the peer's flag row, then waits for the peer's epoch in mine.
 constexpr int NPHASE = 4;
+constexpr unsigned long long FLAG_POISON = ~0ull;  // written into every peer's flag rows by a rank that gave up waiting
+// A missing peer: the reference would block in MPI_Waitall forever (mpicufft_slab.cpp:802-803).  Here the wait
+// gives up after `timeout_cycles` (DFFT_RENDEZVOUS_TIMEOUT_S, default 300 s, 0 = wait forever), records the error
+// and POISONS the flag rows of every group member, so that no rank silently continues on half-delivered slots:
+// every later rendezvous of every member sees the poison, records an error as well, and dfft_plan_wait returns
+// DFFT_ERR_TIMEOUT on all of them (the plan is dead after that and must be destroyed).
 __global__ void rendezvous_kernel(unsigned long long* const* peer_flags, unsigned long long* my_flags, const int* group,
                                   int gsize, int me, int nranks, int phase, unsigned long long epoch, int* err,
                                   long long timeout_cycles) {
@@ -154,15 +166,26 @@ __global__ void rendezvous_kernel(unsigned long long* const* peer_flags, unsigne
     if (q == me) return;
     __threadfence_system();
     unsigned long long* dst = peer_flags[q] + size_t(phase) * nranks + me;
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(epoch) : "memory");
     const unsigned long long* src = my_flags + size_t(phase) * nranks + q;
-    const long long t0 = clock64();
     unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+    if (v == FLAG_POISON) {  // a peer gave up earlier: do not overwrite its poison with my epoch
+        atomicExch(err, 100 + phase);
+        return;
+    }
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(epoch) : "memory");
+    const long long t0 = clock64();
     while (true) {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+        if (v == FLAG_POISON) {
+            atomicExch(err, 100 + phase);
+            break;
+        }
         if (v >= epoch) break;
-        if (clock64() - t0 > timeout_cycles) {
+        if (timeout_cycles > 0 && clock64() - t0 > timeout_cycles) {
             atomicExch(err, 1 + phase);
+            for (int ph = 0; ph < NPHASE; ++ph)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flags[q] + size_t(ph) * nranks + me), "l"(FLAG_POISON) : "memory");
             break;
         }
         __nanosleep(64);
@@ -246,8 +269,10 @@ struct dfft_plan_s {
     int xchg_ctas = 0;                            // SMs given to the exchange pass in overlapped schedules
     int blocked_ch = 0;                           // > 0: slab forward keeps the y->x intermediate as [b/CH][Nx][CH]
     int xchg_tile_pref = 2;                       // tile preference of passes that store into other GPUs (2 = wide rows)
+    long long rendezvous_timeout_cycles = 0;      // device clock cycles a rendezvous waits for a peer (0 = forever)
     int bulk_store = 0;                           // experimental: exchanging y pass stores with cp.async.bulk (DFFT_BULK_STORE=1)
     cudaStream_t own_stream = nullptr, last_stream = nullptr;  // last_stream: stream of the last exec
+    cudaEvent_t entry_ev = nullptr;  // synchronous execs: "everything the caller queued on the legacy default stream"
     Tables tabs;
     // schedules: [fwd/inv][d-1]
     Schedule sched[2][3];
@@ -1166,6 +1191,23 @@ static int nccl_allgather_bytes(dfft_plan_s* p, const void* mine, size_t bytes, 
     return DFFT_SUCCESS;
 }
 
+// Base address and size of the allocation that contains `ptr` (driver API cuMemGetAddressRange, resolved at run time
+// through the runtime so that libdfft.so does not link libcuda).
+static bool alloc_range(const void* ptr, unsigned long long* base, size_t* span) {
+    typedef int (*fn_t)(unsigned long long*, size_t*, unsigned long long);
+    static fn_t fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess || !f) {
+            cudaGetLastError();
+            return false;
+        }
+        fn = (fn_t)f;
+    }
+    return fn(base, span, (unsigned long long)ptr) == 0;
+}
+
 static void plan_release_memory(dfft_plan_s* p) {
     for (void* q : p->opened) cudaIpcCloseMemHandle(q);
     p->opened.clear();
@@ -1175,6 +1217,7 @@ static void plan_release_memory(dfft_plan_s* p) {
     p->slot_ptr.clear();
     for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 3; ++b) p->sched[a][b] = Schedule();
+    p->tabs.release_seg_tables();
 }
 
 static int plan_setup_memory(dfft_plan_s* p, void* user_device) {
@@ -1190,19 +1233,33 @@ static int plan_setup_memory(dfft_plan_s* p, void* user_device) {
     p->slot_ptr.assign(p->nslots, std::vector<void*>(P, nullptr));
     for (int s = 0; s < p->nslots; ++s) p->slot_ptr[s][me] = (char*)p->work + size_t(s) * p->slot_bytes;
     if (p->any_direct) {
+        // A caller-supplied work area may sit INSIDE a larger allocation (a tensor of a caching allocator): the IPC
+        // handle then names the whole allocation and cudaIpcOpenMemHandle returns its base on the peer, so the byte
+        // offset of the work area inside its allocation travels with the handle.
         cudaIpcMemHandle_t h;
         cudaError_t e = cudaIpcGetMemHandle(&h, p->work);
         int ok = (e == cudaSuccess) ? 1 : 0;
         if (!ok) cudaGetLastError();
-        struct Rec { cudaIpcMemHandle_t h; int ok; int pad[3]; } rec{};
-        rec.h = h; rec.ok = ok;
+        unsigned long long offset = 0;
+        if (ok) {
+            unsigned long long base = 0;
+            size_t span = 0;
+            if (!alloc_range(p->work, &base, &span)) ok = 0;
+            else {
+                offset = (unsigned long long)p->work - base;
+                if (offset + p->work_bytes > span) ok = 0;  // the area does not fit its allocation
+            }
+        }
+        struct Rec { cudaIpcMemHandle_t h; int ok; int pad; unsigned long long offset; } rec{};
+        rec.h = h; rec.ok = ok; rec.offset = offset;
         std::vector<char> all;
         int rc = nccl_allgather_bytes(p, &rec, sizeof(rec), all);
         if (rc) return rc;
         for (int r = 0; r < P; ++r) {
             const Rec* rr = reinterpret_cast<const Rec*>(all.data()) + r;
             if (!rr->ok) return fail(DFFT_ERR_PEER, "rank " + std::to_string(r) + ": work area is not exportable with cudaIpcGetMemHandle "
-                                                    "(must be the base of a cudaMalloc allocation); use comm_method All2All");
+                                                    "(it must lie inside one cudaMalloc allocation that holds getWorkSizeDevice() bytes from "
+                                                    "the given pointer); use comm_method All2All");
         }
         for (int r = 0; r < P; ++r) {
             if (r == me) continue;
@@ -1214,7 +1271,7 @@ static int plan_setup_memory(dfft_plan_s* p, void* user_device) {
                 return fail(DFFT_ERR_PEER, std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(e));
             }
             p->opened.push_back(mapped);
-            for (int s = 0; s < p->nslots; ++s) p->slot_ptr[s][r] = (char*)mapped + size_t(s) * p->slot_bytes;
+            for (int s = 0; s < p->nslots; ++s) p->slot_ptr[s][r] = (char*)mapped + rr->offset + size_t(s) * p->slot_bytes;
         }
     }
     return DFFT_SUCCESS;
@@ -1312,7 +1369,7 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
             if (G.size() > 1) {
                 const unsigned long long ticket = ++p->ticket[s.phase_id];
                 rendezvous_kernel<<<1, 32 * int((G.size() + 31) / 32), 0, ss>>>(p->peer_flags_d, p->flags, p->groups_d + s.group * P, int(G.size()), me, P,
-                                                                              s.phase_id, ticket, p->err_d, 20000000000LL);
+                                                                              s.phase_id, ticket, p->err_d, p->rendezvous_timeout_cycles);
                 CK_CUDA(cudaGetLastError());
                 ++launches;
             }
@@ -1348,6 +1405,27 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
     return DFFT_SUCCESS;
 }
 
+// The one place that decides which schedule a (direction, d) pair runs — used by exec and by dfft_plan_describe, so
+// the CPU schedule emulation always validates exactly what executes.
+static int get_schedule(dfft_plan_s* p, int inverse, int d, Schedule** out) {
+    Schedule& sc = p->sched[inverse ? 1 : 0][d - 1];
+    if (!sc.built) {
+        g_view_error = false;
+        const bool streams = p->cfg.send_method == DFFT_SEND_STREAMS || (p->g.decomp == DFFT_PENCIL && p->cfg.send_method2 == DFFT_SEND_STREAMS);
+        const bool want_overlap = streams && d == 3 && p->P > 1 && p->g.decomp == DFFT_SLAB_ZY_THEN_X && p->direct2 && p->xchg_ctas >= 0;
+        const bool want_pencil_overlap = streams && d == 3 && !inverse && p->g.decomp == DFFT_PENCIL && p->direct1 && p->direct2 &&
+                                         p->grp[1].size() > 1 && p->grp[2].size() > 1 && p->xchg_ctas >= 0 && pencil_overlap_enabled();
+        int rc;
+        if (want_overlap) rc = build_overlapped_slab(p, inverse ? 1 : 0, sc);
+        else if (want_pencil_overlap) rc = build_overlapped_pencil(p, sc);
+        else rc = build_schedule(p, inverse ? 1 : 0, d, sc);
+        if (rc) return rc;
+        if (g_view_error) return fail(DFFT_ERR_STATE, "internal: segments of one view disagree on the axis stride");
+    }
+    *out = &sc;
+    return DFFT_SUCCESS;
+}
+
 static int timer_gather(dfft_plan_s* p);
 static int exec_common(dfft_plan_t p, void* out, const void* in, int inverse, int d, int need_transform, void* stream, bool sync) {
     // sync == true: the plain calls run on the plan's own stream; _async calls use exactly the stream given
@@ -1359,21 +1437,19 @@ static int exec_common(dfft_plan_t p, void* out, const void* in, int inverse, in
     if (d < 1 || d > 3) return fail(DFFT_ERR_INVALID, "d must be 1, 2 or 3");
     if (!out || !in) return fail(DFFT_ERR_INVALID, "null buffer");
     CK_CUDA(cudaSetDevice(p->comm->device));
-    Schedule& sc = p->sched[inverse ? 1 : 0][d - 1];
-    if (!sc.built) {
-        g_view_error = false;
-        int rc = DFFT_SUCCESS;
-        const bool want_overlap = p->cfg.send_method == DFFT_SEND_STREAMS && d == 3 && p->P > 1 && p->g.decomp == DFFT_SLAB_ZY_THEN_X &&
-                                  p->direct2 && p->xchg_ctas >= 0;
-        const bool want_pencil_overlap = p->cfg.send_method == DFFT_SEND_STREAMS && d == 3 && !inverse && p->g.decomp == DFFT_PENCIL &&
-                                         p->direct1 && p->direct2 && p->grp[1].size() > 1 && p->grp[2].size() > 1 && pencil_overlap_enabled();
-        if (want_overlap) rc = build_overlapped_slab(p, inverse ? 1 : 0, sc);
-        else if (want_pencil_overlap) rc = build_overlapped_pencil(p, sc);
-        else rc = build_schedule(p, inverse ? 1 : 0, d, sc);
+    Schedule* scp = nullptr;
+    {
+        int rc = get_schedule(p, inverse, d, &scp);
         if (rc) return rc;
-        if (g_view_error) return fail(DFFT_ERR_STATE, "internal: segments of one view disagree on the axis stride");
     }
+    Schedule& sc = *scp;
     cudaStream_t st = sync ? p->own_stream : (cudaStream_t)stream;
+    if (sync) {
+        // explicit edge from the legacy default stream (belt and braces on top of the blocking-stream semantics; it
+        // also covers callers whose own streams are blocking streams, which the legacy stream itself waits for)
+        CK_CUDA(cudaEventRecord(p->entry_ev, cudaStreamLegacy));
+        CK_CUDA(cudaStreamWaitEvent(st, p->entry_ev, 0));
+    }
     int rc = run_schedule(p, sc, out, in, st);
     if (rc) return rc;
     if (!sync) return DFFT_SUCCESS;
@@ -1599,6 +1675,9 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         // NVLink store efficiency grows with the contiguous run per row: 64-byte rows reach 434 GB/s per direction,
         // 128-byte rows 700 GB/s, 2 KB runs 704 GB/s (profiles/r01_8gpu, r01_bench_n2_*): exchanging passes prefer the
         // wide tile even though it is slower as a purely local pass.  DFFT_XCHG_WIDE=0 keeps the narrow tile.
+        const char* et = getenv("DFFT_RENDEZVOUS_TIMEOUT_S");
+        const double tsec = et ? atof(et) : 300.0;
+        p->rendezvous_timeout_cycles = tsec > 0 ? (long long)(tsec * 1.9e9) : 0;  // clock64 ticks at <= 1.965 GHz
         const char* ebs = getenv("DFFT_BULK_STORE");
         p->bulk_store = (ebs && atoi(ebs) != 0) ? 1 : 0;
         const char* ew = getenv("DFFT_XCHG_WIDE");
@@ -1623,7 +1702,12 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         *plan = p;
         return DFFT_SUCCESS;
     }
-    cudaError_t ce = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
+    // The plan's own stream is a BLOCKING stream: like the reference's cuFFT execs on the legacy default stream
+    // (mpicufft_slab.cpp:788-807) the synchronous dfft_exec_* calls are ordered behind everything the caller queued on
+    // the default stream before the call — a pageable cudaMemcpy whose DMA is still in flight, a kernel that is still
+    // filling `in` (the reference's own testcase 4 does exactly that: random_dist_default.cu:719-724).
+    cudaError_t ce = cudaStreamCreate(&p->own_stream);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&p->entry_ev, cudaEventDisableTiming);
     if (ce != cudaSuccess) { delete p; return fail(DFFT_ERR_CUDA, "cudaStreamCreate failed"); }
     {
         int lo = 0, hi = 0;
@@ -1689,6 +1773,7 @@ int dfft_plan_destroy(dfft_plan_t p) {
         if (p->aux[a]) cudaStreamDestroy(p->aux[a]);
     }
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    if (p->entry_ev) cudaEventDestroy(p->entry_ev);
     delete p;
     return DFFT_SUCCESS;
 }
@@ -1724,7 +1809,11 @@ int dfft_plan_wait(dfft_plan_t p) {
     CK_CUDA(cudaMemcpy(&err, p->err_d, sizeof(int), cudaMemcpyDeviceToHost));
     if (err) {
         cudaMemset(p->err_d, 0, sizeof(int));
-        return fail(DFFT_ERR_TIMEOUT, "device rendezvous timed out in phase " + std::to_string(err - 1) + " (a peer rank did not arrive)");
+        if (err >= 100)
+            return fail(DFFT_ERR_TIMEOUT, "a peer rank gave up waiting at a device rendezvous (phase " + std::to_string(err - 100) +
+                                              "); results are invalid and the plan must be destroyed");
+        return fail(DFFT_ERR_TIMEOUT, "device rendezvous timed out in phase " + std::to_string(err - 1) +
+                                          " (a peer rank did not arrive; DFFT_RENDEZVOUS_TIMEOUT_S); results are invalid and the plan must be destroyed");
     }
     return DFFT_SUCCESS;
 }
@@ -1852,17 +1941,12 @@ static void json_view(std::string& o, const View& v, const Tables& T) {
 }
 int dfft_plan_describe(dfft_plan_t p, int inverse, int d, char* buf, size_t capacity, size_t* needed) {
     if (!p || d < 1 || d > 3) return fail(DFFT_ERR_INVALID, "bad arguments");
-    Schedule& sc = p->sched[inverse ? 1 : 0][d - 1];
-    if (!sc.built) {
-        g_view_error = false;
-        const bool want_overlap = p->cfg.send_method == DFFT_SEND_STREAMS && d == 3 && p->P > 1 && p->g.decomp == DFFT_SLAB_ZY_THEN_X && p->direct2;
-        const bool want_pencil_overlap = p->cfg.send_method == DFFT_SEND_STREAMS && d == 3 && !inverse && p->g.decomp == DFFT_PENCIL &&
-                                         p->direct1 && p->direct2 && p->grp[1].size() > 1 && p->grp[2].size() > 1 && pencil_overlap_enabled();
-        int rc = want_overlap ? build_overlapped_slab(p, inverse ? 1 : 0, sc)
-                              : (want_pencil_overlap ? build_overlapped_pencil(p, sc) : build_schedule(p, inverse ? 1 : 0, d, sc));
+    Schedule* scp = nullptr;
+    {
+        int rc = get_schedule(p, inverse, d, &scp);
         if (rc) return rc;
-        if (g_view_error) return fail(DFFT_ERR_STATE, "internal: segments of one view disagree on the axis stride");
     }
+    Schedule& sc = *scp;
     std::string o = "{\"rank\":" + std::to_string(p->rank) + ",\"esize\":" + std::to_string(p->esize) + ",\"slot_bytes\":" + std::to_string(p->slot_bytes) +
                     ",\"nslots\":" + std::to_string(p->nslots) + ",\"overlapped\":" + (sc.overlapped ? "true" : "false") + ",\"slots\":[";
     for (int s_ = 0; s_ < p->nslots; ++s_) {

@@ -65,7 +65,16 @@ enum PassKind { PASS_C2C_CONTIG = 0, PASS_C2C_TILED = 1, PASS_R2C = 2, PASS_C2R 
 // ---- tile shape choices (compile time) -----------------------------------------------------------
 template <typename T, int LOG2N>
 struct Shape {
-    static constexpr int LOG2E = LOG2N < 4 ? LOG2N : 4;
+    // points per thread: 2^LOG2E_MAX (experiment knobs DFFT_LOG2E_F64 / DFFT_LOG2E_F32; 16 points = radix-16
+    // butterflies and ~120 registers in f64, 8 points = radix-8 and <= 64 registers, i.e. twice the resident warps)
+#ifndef DFFT_LOG2E_F64
+#define DFFT_LOG2E_F64 4
+#endif
+#ifndef DFFT_LOG2E_F32
+#define DFFT_LOG2E_F32 4
+#endif
+    static constexpr int LOG2E_MAX = sizeof(T) == 8 ? DFFT_LOG2E_F64 : DFFT_LOG2E_F32;
+    static constexpr int LOG2E = LOG2N < LOG2E_MAX ? LOG2N : LOG2E_MAX;
     static constexpr int N = 1 << LOG2N;
     static constexpr int TPL = N >> LOG2E;
     // CONTIG: lines per CTA.  Measured on B200 (tools/axis_bench.py): f64 lines of >= 512 points run 6-9 % faster
@@ -103,9 +112,10 @@ struct Shape {
 // Resident CTAs per SM the register allocator must leave room for: 128 registers per thread for f64 and 64 for
 // f32 (16 points per thread) — without it the grid-stride version of the f32 kernels drifted to 90+ registers and
 // lost its second CTA per SM (tiled y pass 5300 -> 3850 GB/s).
-template <typename T>
+template <typename T, int LOG2E = 4>
 constexpr int min_ctas_per_sm(int threads) {
-    return (65536 / (threads * (sizeof(T) == 8 ? 128 : 64))) < 1 ? 1 : (65536 / (threads * (sizeof(T) == 8 ? 128 : 64)));
+    constexpr int regs = (sizeof(T) == 8 ? 128 : 64) >> (LOG2E >= 4 ? 0 : 1);  // 8 points per thread: half the budget
+    return (65536 / (threads * regs)) < 1 ? 1 : (65536 / (threads * regs));
 }
 
 template <typename T>
@@ -266,7 +276,7 @@ struct TileCoord {
 // (FftParams::max_ctas) it is persistent and occupies only that many CTA slots, which is how the overlapped
 // schedule leaves the rest of the GPU to the other passes.
 template <typename T, int LOG2N, int LOG2E, int TB, bool TILED, bool INV>
-__global__ void __launch_bounds__((1 << (LOG2N - LOG2E)) * TB, min_ctas_per_sm<T>((1 << (LOG2N - LOG2E)) * TB))
+__global__ void __launch_bounds__((1 << (LOG2N - LOG2E)) * TB, min_ctas_per_sm<T, LOG2E>((1 << (LOG2N - LOG2E)) * TB))
 fft_c2c_kernel(const __grid_constant__ FftParams p) {
     using C = CtaFft<T, LOG2N, LOG2E, TB, TILED>;
     using LA = LineAccess<T, C::LINES>;
@@ -370,7 +380,7 @@ fft_c2c_kernel(const __grid_constant__ FftParams p) {
 // issues no store instructions.  Requirements (checked by the launcher): out.sN == TB == B, unpadded tile rows,
 // single-segment input.  Not timed on hardware yet.
 template <typename T, int LOG2N, int LOG2E, int TB, bool INV>
-__global__ void __launch_bounds__((1 << (LOG2N - LOG2E)) * TB, min_ctas_per_sm<T>((1 << (LOG2N - LOG2E)) * TB))
+__global__ void __launch_bounds__((1 << (LOG2N - LOG2E)) * TB, min_ctas_per_sm<T, LOG2E>((1 << (LOG2N - LOG2E)) * TB))
 fft_c2c_bulk_kernel(const __grid_constant__ FftParams p) {
     using C = CtaFft<T, LOG2N, LOG2E, TB, true>;
     using LA = LineAccess<T, 1>;
@@ -539,7 +549,7 @@ fft_c2c_pipe_kernel(const __grid_constant__ FftParams p) {
 // The real line is read as M complex points z[m] = x[2m] + i x[2m+1], transformed with the length-M
 // core and split into even/odd spectra in shared memory:  X[k] = Xe[k] + W_2M^k Xo[k].
 template <typename T, int LOG2M, int LOG2E, int TB>
-__global__ void __launch_bounds__((1 << (LOG2M - LOG2E)) * TB, min_ctas_per_sm<T>((1 << (LOG2M - LOG2E)) * TB))
+__global__ void __launch_bounds__((1 << (LOG2M - LOG2E)) * TB, min_ctas_per_sm<T, LOG2E>((1 << (LOG2M - LOG2E)) * TB))
 fft_r2c_kernel(const __grid_constant__ FftParams p) {
     using C = CtaFft<T, LOG2M, LOG2E, TB, false>;
     using LA = LineAccess<T, C::LINES>;
@@ -595,7 +605,7 @@ fft_r2c_kernel(const __grid_constant__ FftParams p) {
 
 // ---- C2R pass (CONTIG): M+1 complex points -> real line of 2M points, unnormalised -----------------------
 template <typename T, int LOG2M, int LOG2E, int TB>
-__global__ void __launch_bounds__((1 << (LOG2M - LOG2E)) * TB, min_ctas_per_sm<T>((1 << (LOG2M - LOG2E)) * TB))
+__global__ void __launch_bounds__((1 << (LOG2M - LOG2E)) * TB, min_ctas_per_sm<T, LOG2E>((1 << (LOG2M - LOG2E)) * TB))
 fft_c2r_kernel(const __grid_constant__ FftParams p) {
     using C = CtaFft<T, LOG2M, LOG2E, TB, false>;
     using LA = LineAccess<T, C::LINES>;

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--prec", default="f64")
     ap.add_argument("--elems", type=int, default=28)  # total complex elements = 2^elems (f64: 4 GiB)
     ap.add_argument("--sizes", default="128,256,512,1024,2048,4096")
+    ap.add_argument("--tag", default="")
+    ap.add_argument("--no-r2c", action="store_true")
     args = ap.parse_args()
     prec = dfft.F64 if args.prec == "f64" else dfft.F32
     cdt = torch.complex128 if prec == dfft.F64 else torch.complex64
@@ -55,7 +57,19 @@ def main():
             gbs = 2 * tot * es / t / 1e6
             res.append(dict(kind=label, n=n, ms=t, gbs=gbs))
             print(f"{label} n={n:5d} a={a:6d} b={b:8d} {t:8.3f} ms {gbs:7.0f} GB/s", flush=True)
-        if prec == dfft.F64 or True:
+        # the slab's x pass on the blocked hand-over layout [nz/CH][n][oy][CH] -> out [n][oy][nz] (oy = 128)
+        for ch in (4, 8):
+            oy = 128
+            nz = tot // (n * oy)
+            if nz < 4 * ch:
+                continue
+            ins = [ch, n * oy * ch, oy * ch]
+            outs = [nz, ch, oy * nz]
+            t = timeit(lambda: dfft.fft1d_general(prec, dfft.FORWARD, n, oy, nz // ch, ch, y, outs, x, ins, s))
+            gbs = 2 * tot * es / t / 1e6
+            res.append(dict(kind=f"tiled-xb{ch}", n=n, ms=t, gbs=gbs))
+            print(f"tiled-xb{ch} n={n:5d} oy={oy} nz={nz:6d} {t:8.3f} ms {gbs:7.0f} GB/s", flush=True)
+        if not args.no_r2c:
             xr = x.view(torch.float64 if prec == dfft.F64 else torch.float32)
             nzo = n // 2 + 1
             lines_r = (2 * tot) // n
@@ -67,7 +81,7 @@ def main():
                 res.append(dict(kind="r2c", n=n, ms=t, gbs=gbs))
                 del out
     os.makedirs("gpurun_out", exist_ok=True)
-    with open(f"gpurun_out/axis_bench_{args.prec}.json", "w") as f:
+    with open(f"gpurun_out/axis_bench_{args.prec}{args.tag}.json", "w") as f:
         json.dump(res, f, indent=1)
 
 
