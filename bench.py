@@ -32,6 +32,17 @@ sys.path.insert(0, ROOT)
 WEAK_SHAPES = {1: (512, 512, 512), 2: (1024, 512, 512), 4: (1024, 1024, 512), 8: (1024, 1024, 1024)}
 
 
+def workload_name(shape, prec="f64", transform="c2c", decomp="slab"):
+    """config.workload — the SAME string in both arms (ours and --impl reference)."""
+    return (f"{shape[0]}x{shape[1]}x{shape[2]} complex-{'double' if prec == 'f64' else 'float'} "
+            f"{'C2C' if transform == 'c2c' else 'R2C'} forward 3D FFT, {decomp} decomposition")
+
+
+def metric_name(transform="c2c"):
+    return ("3D FFT GFLOP/s (5*Ntot*log2(Ntot)/t, complex-double forward)" if transform == "c2c"
+            else "3D FFT GFLOP/s (2.5*Ntot*log2(Ntot)/t, R2C forward)")
+
+
 def flops_c2c(shape):
     n = shape[0] * shape[1] * shape[2]
     return 5.0 * n * math.log2(n)
@@ -100,13 +111,33 @@ class ClockSampler:
 _CPU_INPUT = {}
 
 
-def cpu_fft_sample(shape, reps=1):
-    """The CPU arm: oracle port = pocketfft (scipy.fft.fftn, all host cores) on complex128.
-    Returns (seconds per transform, cores, sample description).  The synthetic input is generated once."""
+def claim_all_cores():
+    """The CPU arm must use every host core it can.  Launchers clamp it: torchrun exports OMP_NUM_THREADS=1 and a
+    parent may have pinned this process.  Undo both before numpy / scipy are imported; report what we got."""
+    n = os.cpu_count() or 1
+    try:
+        os.sched_setaffinity(0, range(n))
+    except Exception:
+        pass
+    try:
+        usable = len(os.sched_getaffinity(0))
+    except Exception:
+        usable = n
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[k] = str(usable)
+    return usable
+
+
+def cpu_fft_sample(shape, reps=1, cores=None):
+    """The CPU arm: oracle port = pocketfft (scipy.fft.fftn, all usable host cores) on complex128.
+    Returns (seconds per transform, cores asked for, sample description, effective parallelism = CPU time / wall time).
+    The synthetic input is generated once."""
+    import resource
+
     import numpy as np
     import scipy.fft as sfft
 
-    cores = os.cpu_count() or 1
+    cores = cores or claim_all_cores()
     x = _CPU_INPUT.get(shape)
     if x is None:
         rng = np.random.default_rng(0)
@@ -115,18 +146,22 @@ def cpu_fft_sample(shape, reps=1):
         x.imag = rng.random(shape) * 255
         _CPU_INPUT.clear()
         _CPU_INPUT[shape] = x
-    best = None
+    best, par = None, None
     for _ in range(reps):
+        r0 = resource.getrusage(resource.RUSAGE_SELF)
         t0 = time.perf_counter()
         y = sfft.fftn(x, workers=cores)
         dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
+        r1 = resource.getrusage(resource.RUSAGE_SELF)
+        if best is None or dt < best:
+            best = dt
+            par = ((r1.ru_utime - r0.ru_utime) + (r1.ru_stime - r0.ru_stime)) / dt
         del y
-    return best, cores, f"scipy.fft.fftn {shape[0]}x{shape[1]}x{shape[2]} complex128, workers={cores}"
+    return best, cores, f"scipy.fft.fftn {shape[0]}x{shape[1]}x{shape[2]} complex128, workers={cores}", par
 
 
 def bounded_cpu_shape(shape):
-    # cap the CPU sample at 512^3 points (about 5-15 s of pocketfft on 8 cores); GFLOP/s is size-normalised
+    # cap the CPU sample at 512^3 points (a few seconds of pocketfft on a host's cores); GFLOP/s is size-normalised
     s = list(shape)
     while s[0] * s[1] * s[2] > 512 ** 3:
         k = max(range(3), key=lambda i: s[i])
@@ -138,29 +173,138 @@ def run_reference(args, shape):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = claim_all_cores()
     cshape = bounded_cpu_shape(shape)
     for _ in range(args.warmup):
-        cpu_fft_sample(cshape)
+        cpu_fft_sample(cshape, cores=cores)
     t0 = time.perf_counter()
-    secs = []
+    secs, pars = [], []
     for _ in range(args.steps):
-        sec, cores, desc = cpu_fft_sample(cshape)
+        sec, cores, desc, par = cpu_fft_sample(cshape, cores=cores)
         secs.append(sec)
+        pars.append(par)
     total = time.perf_counter() - t0
     sec = sum(secs) / len(secs)      # transform time only (input generation is outside the timed region)
     ms = sec * 1e3
     val = flops_c2c(cshape) / sec / 1e9
+    sample = desc if cshape == tuple(shape) else desc + f" (bounded sample of the {shape[0]}x{shape[1]}x{shape[2]} workload; GFLOP/s is size-normalised)"
     line = {
-        "impl": "reference", "metric": "3D FFT GFLOP/s (5*Ntot*log2(Ntot)/t, complex-double forward)", "value": val, "unit": "GFLOP/s",
+        "impl": "reference", "metric": metric_name("c2c"), "value": val, "unit": "GFLOP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{shape[0]}x{shape[1]}x{shape[2]} complex-double forward 3D FFT", "cpu_sample": desc,
+        "config": {"workload": workload_name(shape, args.prec, args.transform, args.decomp), "cpu_sample": sample,
+                   "threads_used": cores, "threads_effective": sum(pars) / len(pars), "host_cpus": os.cpu_count(),
                    "note": "the reference has no CPU path (MPI+cuFFT only, SURVEY.md F1); this arm is the oracle port, pocketfft on the host cores"},
-        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": total,
     }
     print(json.dumps(line), flush=True)
+
+
+
+def parity_check(dfft, make_plan_for, comm_world, rank, world, local, prec, transform, decomp, full_plan, full_in, full_out):
+    """Driver-visible correctness BEFORE the timed region, on every rank:
+      (a) a 256-point-edge global grid of the same decomposition / precision / exchange path, filled with the oracle's
+          index-hashed input, each rank's output block against numpy's 3D transform (the oracle);
+      (b) at the full workload size, on the very buffers that are timed: DC bin = sum of the input, and Parseval
+          (sum |X|^2 = N * sum |x|^2; R2C: Hermitian weights) reduced over all ranks.
+    Returns a dict; ok == False makes bench.py exit non-zero."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from oracle import dft_oracle as O
+
+    f64 = prec == "f64"
+    tol = 1e-10 if f64 else 1e-5
+    c2c = transform == "c2c"
+    res = {"tolerance": tol}
+    # (a) small global grid against the oracle
+    small = (256, 256, 256) if world <= 8 else (512, 256, 256)
+    plan, _ = make_plan_for(small)
+    isz, ist, osz, ost = plan.getInSize(), plan.getInStart(), plan.getOutSize(), plan.getOutStart()
+    cdt = torch.complex128 if f64 else torch.complex64
+    es = 16 if f64 else 8
+    if c2c:
+        xg = O.complex_input(small)
+        ref = O.fft_c2c(xg)
+        xin = torch.from_numpy(np.ascontiguousarray(O.block(xg, ist, isz)).astype(np.complex128 if f64 else np.complex64)).cuda()
+    else:
+        xg = O.real_input(small)
+        ref = O.fft_r2c(xg)
+        xin = torch.from_numpy(np.ascontiguousarray(O.block(xg, ist, isz)).astype(np.float64 if f64 else np.float32)).cuda()
+    out = torch.empty(plan.getDomainSize() // es, dtype=cdt, device="cuda")
+    n_out = osz[0] * osz[1] * osz[2]
+    stream = torch.cuda.current_stream()
+    if c2c:
+        plan.execC2C(out, xin, dfft.FORWARD, stream=stream)
+    else:
+        plan.execR2C(out, xin, stream=stream)
+    plan.wait()
+    got = out[:n_out].cpu().numpy().reshape(osz)
+    blk = O.block(ref, ost, osz)
+    err = float(np.linalg.norm((got - blk).ravel()) / np.linalg.norm(blk.ravel()))
+    # inverse of the oracle's block must give back the input block (unnormalised)
+    back = torch.empty_like(xin)
+    spec = torch.zeros_like(out)
+    spec[:n_out] = torch.from_numpy(np.ascontiguousarray(blk).astype(np.complex128 if f64 else np.complex64)).cuda().reshape(-1)
+    if c2c:
+        plan.execC2C(back, spec, dfft.INVERSE, stream=stream)
+    else:
+        plan.execC2R(back, spec, stream=stream)
+    plan.wait()
+    nsm = float(small[0] * small[1] * small[2])
+    xin_h = xin.cpu().numpy().astype(np.complex128 if c2c else np.float64)
+    err_inv = float(np.linalg.norm((back.cpu().numpy() / nsm - xin_h).ravel()) / np.linalg.norm(xin_h.ravel()))
+    plan.destroy()
+    del out, spec, back, xin
+    t = torch.tensor([err, err_inv], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res["small_grid"] = {"shape": list(small), "rel_l2_forward_max_over_ranks": float(t[0]), "rel_l2_inverse_max_over_ranks": float(t[1]),
+                         "checker": "numpy fftn / rfftn on the oracle's index-hashed input (oracle/dft_oracle.py)"}
+    ok = float(t[0]) < tol and float(t[1]) < tol
+    # (b) full size, the timed buffers
+    osz = full_plan.getOutSize()
+    ost = full_plan.getOutStart()
+    n_out = osz[0] * osz[1] * osz[2]
+    if c2c:
+        full_plan.execC2C(full_out, full_in, dfft.FORWARD, stream=stream)
+    else:
+        full_plan.execR2C(full_out, full_in, stream=stream)
+    full_plan.wait()
+    X = full_out[:n_out].reshape(osz)
+    sx = full_in.sum().to(torch.complex128)
+    e_in = (full_in.abs().double() ** 2).sum() if c2c else (full_in.double() ** 2).sum()
+    if c2c:
+        e_out = (X.real.double() ** 2 + X.imag.double() ** 2).sum()
+    else:
+        # Hermitian half spectrum: bins kz = 0 and kz = Nz/2 count once, the others twice
+        p2 = X.real.double() ** 2 + X.imag.double() ** 2
+        w = torch.full((osz[2],), 2.0, device="cuda", dtype=torch.float64)
+        gz0 = ost[2]
+        nzc_global = full_plan.global_size.Nz // 2 + 1
+        for k in range(osz[2]):
+            if gz0 + k == 0 or gz0 + k == nzc_global - 1:
+                w[k] = 1.0
+        e_out = (p2 * w).sum()
+    dc = X[0, 0, 0].to(torch.complex128) if (ost[0] == 0 and ost[1] == 0 and ost[2] == 0) else torch.zeros((), dtype=torch.complex128, device="cuda")
+    v = torch.stack([sx.real, sx.imag, e_in.to(torch.float64), e_out.to(torch.float64), dc.real, dc.imag])
+    if world > 1:
+        dist.all_reduce(v)
+    gs = full_plan.global_size
+    ntot = float(gs.Nx) * gs.Ny * gs.Nz
+    s_in = complex(float(v[0]), float(v[1]))
+    dcv = complex(float(v[4]), float(v[5]))
+    dc_err = abs(dcv - s_in) / abs(s_in)
+    pars_err = abs(float(v[3]) / (ntot * float(v[2])) - 1.0)
+    res["full_size"] = {"shape": [gs.Nx, gs.Ny, gs.Nz], "dc_bin_rel_err": dc_err, "parseval_rel_err": pars_err,
+                        "note": "on the timed buffers: X[0,0,0] == sum(x), sum|X|^2 == N sum|x|^2, reduced over all ranks"}
+    tol_full = 1e-10 if f64 else 2e-4  # f32 sums over 2^29+ values in float32 accumulate rounding
+    ok = ok and dc_err < tol_full and pars_err < tol_full
+    res["ok"] = bool(ok)
+    return res
 
 
 def main(argv=None):
@@ -179,6 +323,7 @@ def main(argv=None):
     ap.add_argument("--transform", default="c2c", choices=["c2c", "r2c"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the correctness checks in front of the timed region")
     args = ap.parse_args(argv)
     args.warmup = max(args.warmup, 3) if args.impl == "dfft" else args.warmup
 
@@ -215,7 +360,7 @@ def main(argv=None):
     cfg = dfft.Configurations(comm_method=cm, comm_method2=cm, send_method=sm)
     c2c = args.transform == "c2c"
 
-    def make_plan(config):
+    def make_plan(config, shape=shape):
         if args.decomp == "pencil":
             p1 = args.p1 or (2 if world >= 2 else 1)
             p2 = args.p2 or world // p1
@@ -263,6 +408,13 @@ def main(argv=None):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(dfft, lambda shp: make_plan(cfg, shp), comm, rank, world, local, args.prec, args.transform, args.decomp, plan, x, out)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"error": "parity check failed", "parity": parity}), flush=True)
+            sys.exit(3)
     for _ in range(args.warmup):
         step()
     plan.wait()
@@ -373,8 +525,9 @@ def main(argv=None):
     if rank == 0 and world == 1:
         if not args.no_cpu:
             cs = bounded_cpu_shape(shape)
-            sec, cores, desc = cpu_fft_sample(cs, reps=1)
-            cpu = {"value": flops_c2c(cs) / sec / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": desc, "ms": sec * 1e3}
+            sec, cores, desc, par = cpu_fft_sample(cs, reps=1)
+            cpu = {"value": flops_c2c(cs) / sec / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": desc, "ms": sec * 1e3,
+                   "threads_effective": par}
         ref = os.path.join(ROOT, "oracle", "_ref", "libcufft_ref.so")
         if os.path.exists(ref) and c2c:
             try:
@@ -390,10 +543,10 @@ def main(argv=None):
     # host memory, transforms it and copies the spectrum block back; consecutive steps are pipelined (the D2H of
     # step i overlaps the H2D of step i+1), all inside the timed region
     def run_e2e():
-        hin = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+        hin = dfft.pinned_empty(x.numel(), x.dtype, local)   # pages on the GPU's own NUMA node
         hin.copy_(x)
         n_out = osz[0] * osz[1] * osz[2]
-        hout = torch.empty(n_out, dtype=cdt, pin_memory=True)
+        hout = dfft.pinned_empty(n_out, cdt, local)
         hx = dfft.HostExecutor(plan, dfft.FORWARD)
         for _ in range(2):
             hx.submit(hout, hin)
@@ -417,16 +570,16 @@ def main(argv=None):
         chk = float((hout[:1024].cuda() - hx.d_out[(hx.count - 1) & 1][:1024]).abs().max())
         return {"value": fl / (t * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": t, "wall_ms_per_step": wall_ms / ksteps,
                 "h2d_bytes_per_step": int(x.numel() * x.element_size() * world), "d2h_bytes_per_step": int(n_out * es * world),
-                "pipeline": "H2D(i+1) overlaps D2H(i); 2 device buffer sets", "host_equals_device": chk == 0.0}
+                "pipeline": "H2D(i+1) overlaps D2H(i); 2 device buffer sets", "host_equals_device": chk == 0.0,
+                "pinned_numa_cpus": len(dfft.gpu_local_cpus(local) or []) or None}
 
     def make_line(e2e, clocks):
         return {
-            "metric": "3D FFT GFLOP/s (5*Ntot*log2(Ntot)/t, complex-double forward)" if c2c else "3D FFT GFLOP/s (2.5*Ntot*log2(Ntot)/t, R2C forward)",
+            "metric": metric_name(args.transform),
             "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.prec, "data": "synthetic",
-            "config": {"workload": f"{shape[0]}x{shape[1]}x{shape[2]} complex-{'double' if f64 else 'float'} "
-                                   f"{'C2C' if c2c else 'R2C'} forward 3D FFT, {args.decomp} decomposition",
-                       "parallelism": par, "comm_method": args.comm, "send_method": send, "sequential_schedule_ms": seq_ms, "ms_inverse": ms_inverse, "points_per_gpu": int(ntot_local),
+            "config": {"workload": workload_name(shape, args.prec, args.transform, args.decomp),
+                       "parallelism": par, "parity": parity, "comm_method": args.comm, "send_method": send, "sequential_schedule_ms": seq_ms, "ms_inverse": ms_inverse, "points_per_gpu": int(ntot_local),
                        "l2_policy": "inputs (>= 2 GiB per GPU) exceed the 126 MB L2; no flush needed",
                        "gflops_literal_5N3log2N_edge": (5.0 * shape[0] * shape[1] * shape[2] * math.log2(shape[0]) / (ms_step * 1e-3) / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

@@ -544,8 +544,15 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
         // transposition 2: scatter along y over G2 (column of the grid, or all ranks for the slab)
         Step x2;
         const bool t2_a2a = !dir2;
-        const size_t CH = (dir2 && g.decomp == DFFT_SLAB_ZY_THEN_X && !(t1_a2a)) ? size_t(p->blocked_ch) : 0;
+        const size_t CH = (dir2 && !t1_a2a) ? size_t(p->blocked_ch) : 0;  // slab and pencil (second transposition)
         const size_t rem = CH ? nz_j % CH : 0, nzm = nz_j - rem;
+        // every rank emits the same step list: when any rank of the grid has leftover columns the others run the
+        // tail steps as empty passes (B = 0)
+        bool any_rem = false;
+        if (CH) {
+            if (g.decomp == DFFT_PENCIL) { for (size_t v : g.sz.size) any_rem = any_rem || (v % CH != 0); }
+            else any_rem = rem != 0;
+        }
         Step s2t;
         bool have_tail = false;
         if (dir2 && CH) {
@@ -567,7 +574,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
                     return mkseg(eptr(slotp(D2, r), x0_i * nyq * CH, es), (long long)(nyq * CH), (long long)(g.nx * nyq * CH), (long long)CH, g.oy.start[q]);
                 });
             }
-            if (rem) {  // leftover columns z in [nzm, nzc): plain layout [nx][ny_q][rem] behind the blocked part
+            if (any_rem) {  // leftover columns z in [nzm, nzc): plain layout [nx][ny_q][rem] behind the blocked part
                 s2t = s2;
                 have_tail = true;
                 s2t.label = "y pass (tail)";
@@ -613,7 +620,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
             else
                 s3.prm.in = single_view(slotp(D2, me), (long long)CH, (long long)(g.nx * oy_i * CH), (long long)(oy_i * CH));
             s3.prm.out = single_view(nullptr, (long long)nz_j, (long long)CH, (long long)(oy_i * nz_j));
-            if (rem) {
+            if (any_rem) {
                 Step s3t = s3;
                 s3t.label = "x pass (tail)";
                 s3t.phase = nullptr;
@@ -1097,7 +1104,21 @@ static int build_overlapped_pencil(dfft_plan_s* p, Schedule& sc) {
     const size_t NS = min_nz >= 128 ? 4 : (min_nz >= 32 ? 2 : 1);
     Split groups, chunks;
     groups.make(nx_i, NG);
-    chunks.make(nz_j, NS);
+    // blocked hand-over of the second transposition: receiver (q, j) holds [nz_j/CH][nx][ny_q][CH] (+ a plain-layout
+    // tail of nz_j % CH columns), see build_schedule
+    const size_t CH = size_t(p->blocked_ch);
+    const size_t rem = CH ? nz_j % CH : 0, nzm = nz_j - rem;
+    bool any_rem = false;  // ranks without leftover columns run the tail steps as empty passes: same step list everywhere
+    if (CH) for (size_t v : g.sz.size) any_rem = any_rem || (v % CH != 0);
+    if (CH) {
+        Split u;
+        u.make(nzm / CH, std::min<size_t>(NS, nzm / CH));
+        if (u.size.size() != NS) return fail(DFFT_ERR_STATE, "internal: blocked z chunks");
+        chunks.size.clear(); chunks.start.clear();
+        for (size_t c = 0; c < u.size.size(); ++c) { chunks.size.push_back(u.size[c] * CH); chunks.start.push_back(u.start[c] * CH); }
+    } else {
+        chunks.make(nz_j, NS);
+    }
     const unsigned char *tab_z = nullptr, *tab_y = nullptr;
     if (T.seg_table(g.sz, &tab_z) != cudaSuccess || T.seg_table(g.oy, &tab_y) != cudaSuccess) return fail(DFFT_ERR_CUDA, "segment table");
 
@@ -1136,17 +1157,44 @@ static int build_overlapped_pencil(dfft_plan_s* p, Schedule& sc) {
             Step s;
             rc = new_pass(PASS_C2C_TILED, ny, "y pass", s);
             if (rc) return rc;
-            s.prm.A0 = int(npl); s.prm.A1 = 1; s.prm.B = int(zc);
-            s.prm.in = single_view(eptr(slotp(D1, me), pl0 * ny * nz_j + z0, es), (long long)(ny * nz_j), 0, (long long)nz_j);
-            seg_view(s.prm.out, tab_y, G2, [&](int q, int r) {
-                const size_t nyq = g.oy.size[q];
-                return mkseg(eptr(slotp(D2, r), (x0_i + pl0) * nyq * nz_j + z0, es), (long long)(nyq * nz_j), 0, (long long)nz_j, g.oy.start[q]);
-            });
+            if (CH) {
+                s.prm.A0 = int(npl); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
+                s.prm.in = single_view(eptr(slotp(D1, me), pl0 * ny * nz_j + z0, es), (long long)(ny * nz_j), (long long)CH, (long long)nz_j);
+                s.prm.bulk_out = G2.size() > 1 ? p->bulk_store : 0;
+                seg_view(s.prm.out, tab_y, G2, [&](int q, int r) {
+                    const size_t nyq = g.oy.size[q];
+                    return mkseg(eptr(slotp(D2, r), ((z0 / CH) * nx + x0_i + pl0) * nyq * CH, es), (long long)(nyq * CH), (long long)(nx * nyq * CH),
+                                 (long long)CH, g.oy.start[q]);
+                });
+            } else {
+                s.prm.A0 = int(npl); s.prm.A1 = 1; s.prm.B = int(zc);
+                s.prm.in = single_view(eptr(slotp(D1, me), pl0 * ny * nz_j + z0, es), (long long)(ny * nz_j), 0, (long long)nz_j);
+                seg_view(s.prm.out, tab_y, G2, [&](int q, int r) {
+                    const size_t nyq = g.oy.size[q];
+                    return mkseg(eptr(slotp(D2, r), (x0_i + pl0) * nyq * nz_j + z0, es), (long long)(nyq * nz_j), 0, (long long)nz_j, g.oy.start[q]);
+                });
+            }
             s.prm.max_ctas = p->xchg_ctas;
             s.prm.tile_pref = G2.size() > 1 ? p->xchg_tile_pref : 0;
             s.stream = 1;
-            if (gi + 1 == NG) s.record = ev_y[c] = nev++;
+            const bool tail_here = CH && any_rem && c + 1 == NS;
+            if (gi + 1 == NG && !tail_here) s.record = ev_y[c] = nev++;
             sc.steps.push_back(s);
+            if (tail_here) {
+                Step t = s;
+                t.label = "y pass (tail)";
+                t.prm.bulk_out = 0;
+                t.waits.clear();
+                t.record = -1;
+                t.prm.A0 = int(npl); t.prm.A1 = 1; t.prm.B = int(rem);
+                t.prm.in = single_view(eptr(slotp(D1, me), pl0 * ny * nz_j + nzm, es), (long long)(ny * nz_j), 0, (long long)nz_j);
+                seg_view(t.prm.out, tab_y, G2, [&](int q, int r) {
+                    const size_t nyq = g.oy.size[q];
+                    return mkseg(eptr(slotp(D2, r), nx * nyq * nzm + (x0_i + pl0) * nyq * rem, es), (long long)(nyq * rem), 0, (long long)rem, g.oy.start[q]);
+                });
+                if (gi + 1 == NG) t.record = ev_y[c] = nev++;
+                sc.steps.push_back(t);
+            }
         }
     }
     for (size_t c = 0; c < NS; ++c) {
@@ -1157,12 +1205,26 @@ static int build_overlapped_pencil(dfft_plan_s* p, Schedule& sc) {
         Step s;
         rc = new_pass(PASS_C2C_TILED, nx, "x pass", s);
         if (rc) return rc;
-        s.prm.A0 = 1; s.prm.A1 = int(oy_i); s.prm.B = int(zc);
-        s.prm.in = single_view(eptr(slotp(D2, me), z0, es), 0, (long long)nz_j, (long long)(oy_i * nz_j));
-        s.prm.out = single_view((void*)(size_t)(z0 * es), 0, (long long)nz_j, (long long)(oy_i * nz_j));
+        if (CH) {
+            s.prm.A0 = int(oy_i); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
+            s.prm.in = single_view(eptr(slotp(D2, me), (z0 / CH) * nx * oy_i * CH, es), (long long)CH, (long long)(nx * oy_i * CH), (long long)(oy_i * CH));
+            s.prm.out = single_view((void*)(size_t)(z0 * es), (long long)nz_j, (long long)CH, (long long)(oy_i * nz_j));
+        } else {
+            s.prm.A0 = 1; s.prm.A1 = int(oy_i); s.prm.B = int(zc);
+            s.prm.in = single_view(eptr(slotp(D2, me), z0, es), 0, (long long)nz_j, (long long)(oy_i * nz_j));
+            s.prm.out = single_view((void*)(size_t)(z0 * es), 0, (long long)nz_j, (long long)(oy_i * nz_j));
+        }
         s.out_user = 2;
         s.stream = 2;
         sc.steps.push_back(s);
+        if (CH && any_rem && c + 1 == NS) {
+            Step t = s;
+            t.label = "x pass (tail)";
+            t.prm.A0 = int(oy_i); t.prm.A1 = 1; t.prm.B = int(rem);
+            t.prm.in = single_view(eptr(slotp(D2, me), nx * oy_i * nzm, es), (long long)rem, 0, (long long)(oy_i * rem));
+            t.prm.out = single_view((void*)(size_t)(nzm * es), (long long)nz_j, 0, (long long)(oy_i * nz_j));
+            sc.steps.push_back(t);
+        }
     }
     sc.nevents = nev;
     sc.built = true;
@@ -1691,7 +1753,10 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         };
         int ch = int(std::max<size_t>(8, std::max(tile_cols(ny), tile_cols(nx))));
         if (eb) ch = atoi(eb);
-        p->blocked_ch = (decomp == DFFT_SLAB_ZY_THEN_X && ch > 0 && g.nzc >= size_t(4 * ch)) ? ch : 0;
+        size_t min_nz = g.nzc;  // smallest z extent any rank holds between the y and x passes
+        if (decomp == DFFT_PENCIL)
+            for (size_t v : g.sz.size) min_nz = std::min(min_nz, v);
+        p->blocked_ch = ((decomp == DFFT_SLAB_ZY_THEN_X || decomp == DFFT_PENCIL) && ch > 0 && min_nz >= size_t(4 * ch)) ? ch : 0;
     }
     if (dry) {
         // fake, rank-distinct slot addresses: ((rank + 1) << 44) + slot * slot_bytes; user buffers are offsets

@@ -16,23 +16,6 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
 }
 
-// persistent-kernel grid: resident CTAs per SM (queried once per kernel) x SM count
-template <typename K>
-static int persistent_ctas(K kernel, int threads, size_t smem) {
-    int dev = 0, sms = 0, per = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, threads, smem) != cudaSuccess || per < 1) per = 1;
-    return sms * per;
-}
-
-// DFFT_PIPE=1 selects the persistent register-prefetch kernels where the tile shape allows 255 registers
-// per thread (measured slower than two resident CTAs per SM on B200 for most shapes, so off by default).
-static int pipe_mode() {
-    const char* e = getenv("DFFT_PIPE");  // read per launch (cheap) so that one process can compare variants
-    return e ? atoi(e) : 0;
-}
-
 static int wide_tiles() {
     const char* e = getenv("DFFT_WIDE_TILES");
     return e ? atoi(e) : 0;
@@ -50,9 +33,9 @@ static cudaError_t launch_tiled(const FftParams& p, cudaStream_t stream, long lo
     if (p.B <= 0) return cudaSuccess;
     const long long grid = lines * ((p.B + TB - 1) / TB);
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    if constexpr (!C::L::PAD) {
-        // experimental TMA bulk-store variant (see fft_c2c_bulk_kernel): only when the launcher's contract holds
-        if (p.bulk_out && p.in.nseg == 1 && p.out.sN == TB && p.B == TB) {
+    {
+        // TMA bulk-store variant (see fft_c2c_bulk_kernel): only when the launcher's contract holds
+        if (p.bulk_out && p.in.nseg == 1 && p.out.sN == TB && p.B == TB && (TB * sizeof(cx<T>)) % 16 == 0) {
             auto bf = fft_c2c_bulk_kernel<T, LOG2N, LOG2E, TB, false>;
             auto bi = fft_c2c_bulk_kernel<T, LOG2N, LOG2E, TB, true>;
             static cudaError_t onceb = set_smem(bf, C::SMEM_BYTES) != cudaSuccess ? cudaErrorInvalidValue : set_smem(bi, C::SMEM_BYTES);
@@ -60,19 +43,6 @@ static cudaError_t launch_tiled(const FftParams& p, cudaStream_t stream, long lo
             const unsigned gb = unsigned((p.max_ctas > 0 && grid > p.max_ctas) ? p.max_ctas : grid);
             if (p.inverse) bi<<<gb, C::THREADS, C::SMEM_BYTES, stream>>>(p);
             else bf<<<gb, C::THREADS, C::SMEM_BYTES, stream>>>(p);
-            return cudaGetLastError();
-        }
-    }
-    if constexpr (C::THREADS <= (sizeof(T) == 8 ? 256 : 512)) {
-        if (pipe_mode() && p.max_ctas <= 0) {
-            auto pf = fft_c2c_pipe_kernel<T, LOG2N, LOG2E, TB, true, false>;
-            auto pi = fft_c2c_pipe_kernel<T, LOG2N, LOG2E, TB, true, true>;
-            static cudaError_t oncep = set_smem(pf, C::SMEM_BYTES) != cudaSuccess ? cudaErrorInvalidValue : set_smem(pi, C::SMEM_BYTES);
-            if (oncep != cudaSuccess) return oncep;
-            static int ctas = persistent_ctas(pf, C::THREADS, C::SMEM_BYTES);
-            const unsigned g = unsigned(grid < ctas ? grid : ctas);
-            if (p.inverse) pi<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
-            else pf<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
             return cudaGetLastError();
         }
     }
@@ -99,19 +69,6 @@ cudaError_t launch_pass(PassKind kind, const FftParams& p, cudaStream_t stream) 
             if (p.in.sN != 1 || p.out.sN != 1) return cudaErrorInvalidValue;
             const long long grid = (lines + S::TBC - 1) / S::TBC;
             if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-            if constexpr (C::THREADS <= (sizeof(T) == 8 ? 256 : 512)) {
-                if (pipe_mode()) {
-                    auto pf = fft_c2c_pipe_kernel<T, LOG2N, LOG2E, S::TBC, false, false>;
-                    auto pi = fft_c2c_pipe_kernel<T, LOG2N, LOG2E, S::TBC, false, true>;
-                    static cudaError_t oncep = set_smem(pf, C::SMEM_BYTES) != cudaSuccess ? cudaErrorInvalidValue : set_smem(pi, C::SMEM_BYTES);
-                    if (oncep != cudaSuccess) return oncep;
-                    static int ctas = persistent_ctas(pf, C::THREADS, C::SMEM_BYTES);
-                    const unsigned g = unsigned(grid < ctas ? grid : ctas);
-                    if (p.inverse) pi<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
-                    else pf<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
-                    break;
-                }
-            }
             if (p.inverse) ki<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
             else kf<<<unsigned(grid), C::THREADS, C::SMEM_BYTES, stream>>>(p);
             break;

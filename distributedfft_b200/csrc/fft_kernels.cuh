@@ -176,14 +176,6 @@ struct LineAccess {
     }
 };
 
-// table-free address of element (a0, a1, n, b) of a view (used for prefetching the next tile)
-template <typename T>
-__device__ __forceinline__ cx<T>* view_at(const View& v, int a0, int a1, int n, int b) {
-    const int s = v.nseg > 1 ? int(v.seg_of_n[n]) : 0;
-    const Seg& g = v.seg[s];
-    return reinterpret_cast<cx<T>*>(g.base) + (a0 * g.sA0 + a1 * g.sA1 + (long long)(n - g.n0) * v.sN + b);
-}
-
 // ---- the in-CTA transform ---------------------------------------------------------------------------
 template <typename T, int LOG2N, int LOG2E, int TB, bool TILED>
 struct CtaFft {
@@ -386,7 +378,8 @@ fft_c2c_bulk_kernel(const __grid_constant__ FftParams p) {
     using LA = LineAccess<T, 1>;
     using TC = TileCoord<C, true, TB>;
     constexpr int E = C::E, TPL = C::TPL, N = C::N;
-    static_assert(!C::L::PAD, "bulk stores need unpadded tile rows");
+    // the staging copy of the finished tile is written UNPADDED ([n][TB], N*TB elements <= the padded tile) once the
+    // last gather has left the buffer, so narrow (padded) tiles qualify as well
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
     unsigned long long* tab_in = reinterpret_cast<unsigned long long*>(smem_raw + C::TILE_BYTES);
@@ -444,105 +437,6 @@ fft_c2c_bulk_kernel(const __grid_constant__ FftParams p) {
     // all bulk stores of this CTA have been written (not only read from shared memory) before the kernel ends:
     // the rendezvous that follows publishes them to the peers
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-
-// ---- C2C pass, persistent + register prefetch ---------------------------------------------------------
-// One CTA per SM slot loops over tiles; the global loads of tile i+1 are issued into a second register
-// set before the stages of tile i run, so HBM latency overlaps the butterflies instead of being exposed
-// at the start of every CTA (the non-pipelined kernel has ~16 warps/SM and stalls on long scoreboard).
-template <typename T, int LOG2N, int LOG2E, int TB, bool TILED, bool INV>
-__global__ void __launch_bounds__((1 << (LOG2N - LOG2E)) * TB, 1)
-fft_c2c_pipe_kernel(const __grid_constant__ FftParams p) {
-    using C = CtaFft<T, LOG2N, LOG2E, TB, TILED>;
-    using LA = LineAccess<T, C::LINES>;
-    using TC = TileCoord<C, TILED, TB>;
-    constexpr int E = C::E, TPL = C::TPL;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
-    unsigned long long* tab_in = reinterpret_cast<unsigned long long*>(smem_raw + C::TILE_BYTES);
-    unsigned long long* tab_out = tab_in + C::LINES * MAXSEG;
-
-    const long long ntiles = TC::num_tiles(p);
-    const bool in_multi = p.in.nseg > 1, out_multi = p.out.nseg > 1;
-
-    auto prefetch = [&](cx<T> (&r)[E], long long tile) {
-        const TC tc(p, tile);
-        if (tc.valid) {
-            if (!in_multi) {
-                const Seg& g = p.in.seg[0];
-                const cx<T>* q = reinterpret_cast<const cx<T>*>(g.base) + (tc.a0 * g.sA0 + tc.a1 * g.sA1 - (long long)g.n0 * p.in.sN + tc.b);
-                if constexpr (!TILED) {
-                    q += tc.j;
-#pragma unroll
-                    for (int e = 0; e < E; ++e) r[e] = ld_elem<T>(q + e * TPL);
-                } else {
-                    const long long step = (long long)TPL * p.in.sN;
-                    q += (long long)tc.j * p.in.sN;
-#pragma unroll
-                    for (int e = 0; e < E; ++e) { r[e] = ld_elem<T>(q); q += step; }
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < E; ++e) r[e] = ld_elem<T>(view_at<T>(p.in, tc.a0, tc.a1, tc.j + e * TPL, tc.b));
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < E; ++e) r[e] = cx<T>{T(0), T(0)};
-        }
-    };
-
-    cx<T> v[E], nx[E];
-    long long tile = blockIdx.x;
-    if (tile < ntiles) prefetch(nx, tile);
-#pragma unroll 1
-    for (; tile < ntiles; tile += gridDim.x) {
-        const TC tc(p, tile);
-        const int j = tc.j, t = tc.t;
-#pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = INV ? cswap(nx[e]) : nx[e];
-        const long long nt = tile + gridDim.x;
-        if (nt < ntiles) prefetch(nx, nt);
-
-        if (out_multi) {
-            const int line = TILED ? 0 : t;
-            LA::fill_table(p.out, tab_out, line, TILED ? int(threadIdx.x) : j, TILED ? C::THREADS : TPL, tc.a0, tc.a1);
-        }
-        C::template stages<0>(v, j, t, sm, reinterpret_cast<const cx<T>*>(p.tw));
-        if (out_multi) __syncthreads();  // table visible (and, for 1-stage plans, written before use)
-
-        if (tc.valid) {
-            const LA out(p.out, tab_out, TILED ? 0 : t, tc.a0, tc.a1, tc.b);
-            if (!out.multi) {
-                if constexpr (!TILED) {
-                    cx<T>* q = out.p0 + j;
-#pragma unroll
-                    for (int e = 0; e < E; ++e) {
-                        const cx<T> x = v[C::Core::final_slot(e)];
-                        st_elem<T>(q + e * TPL, INV ? cswap(x) : x);
-                    }
-                } else {
-                    const long long step = (long long)TPL * p.out.sN;
-                    cx<T>* q = out.p0 + (long long)j * p.out.sN;
-#pragma unroll
-                    for (int e = 0; e < E; ++e) {
-                        const cx<T> x = v[C::Core::final_slot(e)];
-                        st_elem<T>(q, INV ? cswap(x) : x);
-                        q += step;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const cx<T> x = v[C::Core::final_slot(e)];
-                    st_elem<T>(out.at(j + e * TPL), INV ? cswap(x) : x);
-                }
-            }
-        }
-        // the next iteration's first scatter must not overtake this iteration's last gather, and the
-        // segment table is rewritten: one barrier per tile
-        if constexpr (C::NST > 1) C::sync(t);
-        if (out_multi) __syncthreads();
-    }
 }
 
 // ---- R2C pass (CONTIG): real line of 2M points -> M+1 complex points ------------------------------------

@@ -70,11 +70,159 @@ def full_size_properties(comm, rank, world):
     return fails
 
 
+def _cufft():
+    import ctypes as C
+    path = os.path.join(ROOT, "oracle", "_ref", "libcufft_ref.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    lib.cufft_ref_3d.restype = C.c_int
+    lib.cufft_ref_3d.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int]
+    return lib
+
+
+def full_size_vs_cufft(comm, rank, world):
+    """The reference's testcase 1 at FULL size (random_dist_default.cu:226-459, pencil random_dist_3D.cu:386-403): the
+    distributed result equals one cufftPlan3d transform of the global array on a single GPU.  Rank 0 plays the
+    coordinator: it regenerates every rank's seeded input block, runs cuFFT on the global array and compares each
+    rank's output block (received over NCCL) element by element on the device."""
+    import ctypes as C
+    lib = _cufft()
+    if lib is None:
+        if rank == 0:
+            print("SKIP full-size cuFFT comparison: oracle/_ref/libcufft_ref.so not built", flush=True)
+        return 0
+    weak = {1: (512, 512, 512), 2: (1024, 512, 512), 4: (1024, 1024, 512), 8: (1024, 1024, 1024)}
+    shape = weak.get(world, (512, 512, 512))
+    S, ST = dfft.SendMethod.Sync, dfft.SendMethod.Streams
+    cases = [("slab c2c f64 Streams (config 3)", dfft.MPIcuFFT_Slab, None, "double", "c2c", ST, shape),
+             ("slab r2c f64 Streams (config 5)", dfft.MPIcuFFT_Slab, None, "double", "r2c", ST, shape),
+             ("slab r2c f64 Sync", dfft.MPIcuFFT_Slab, None, "double", "r2c", S, shape),
+             ("z_then_yx c2c f64", dfft.MPIcuFFT_Slab_Z_Then_YX, None, "double", "c2c", S, shape)]
+    if world >= 4:
+        pshape = (2048, 2048, 1024) if world == 8 else (1024, 1024, 1024)
+        grid = (2, world // 2)
+        cases.append((f"pencil {grid[0]}x{grid[1]} c2c f32 Sync (config 4)", dfft.MPIcuFFT_Pencil, grid, "float", "c2c", S, pshape))
+        cases.append((f"pencil {grid[0]}x{grid[1]} c2c f32 Streams (config 4)", dfft.MPIcuFFT_Pencil, grid, "float", "c2c", ST, pshape))
+        cases.append((f"pencil {grid[1]}x{grid[0]} r2c f64", dfft.MPIcuFFT_Pencil, (grid[1], grid[0]), "double", "r2c", S, shape))
+    elif world == 2:
+        cases.append(("pencil 1x2 r2c f64", dfft.MPIcuFFT_Pencil, (1, 2), "double", "r2c", S, shape))
+        cases.append(("pencil 2x1 c2c f32 Streams", dfft.MPIcuFFT_Pencil, (2, 1), "float", "c2c", ST, shape))
+    fails = 0
+    for name, cls, grid, prec, tr, snd, shp in cases:
+        f64 = prec == "double"
+        c2c = tr == "c2c"
+        rdt, cdt = (torch.float64, torch.complex128) if f64 else (torch.float32, torch.complex64)
+        tol = 1e-10 if f64 else 1e-5
+        cfg = dfft.Configurations(send_method=snd, send_method2=snd)
+        plan = cls(cfg, comm, precision=prec, transform=tr)
+        plan.initFFT(dfft.GlobalSize(*shp), dfft.Pencil_Partition(*grid) if grid else None, True)
+        decomp = plan._decomp
+        p1, p2 = (grid if grid else (world, 1))
+        trn = dfft.C2C if c2c else dfft.R2C
+
+        def gen(r, size):
+            g = torch.Generator(device="cuda").manual_seed(4242 + r)
+            if c2c:
+                return torch.complex(torch.rand(size, generator=g, device="cuda", dtype=rdt) * 255, torch.rand(size, generator=g, device="cuda", dtype=rdt) * 255)
+            return torch.rand(size, generator=g, device="cuda", dtype=rdt) * 255
+
+        isz, osz = plan.getInSize(), plan.getOutSize()
+        x = gen(rank, isz)
+        es = 16 if f64 else 8
+        out = torch.empty(plan.getDomainSize() // es, dtype=cdt, device="cuda")
+        if c2c:
+            plan.execC2C(out, x, dfft.FORWARD)
+        else:
+            plan.execR2C(out, x)
+        n_out = osz[0] * osz[1] * osz[2]
+        nzc = shp[2] if c2c else shp[2] // 2 + 1
+        worst = torch.zeros(2, device="cuda", dtype=torch.float64)  # [sum |diff|^2, sum |ref|^2]
+        if rank == 0:
+            xg = torch.empty(shp, dtype=x.dtype, device="cuda")
+            for r in range(world):
+                sz, st0 = dfft.layout(decomp, trn, *shp, p1, p2, r, 0)
+                xg[st0[0]:st0[0] + sz[0], st0[1]:st0[1] + sz[1], st0[2]:st0[2] + sz[2]] = x if r == 0 else gen(r, sz)
+            ref = torch.empty((shp[0], shp[1], nzc), dtype=cdt, device="cuda")
+            ms = C.c_float()
+            rc = lib.cufft_ref_3d(1 if f64 else 0, 0 if c2c else 2, shp[0], shp[1], shp[2], ref.data_ptr(), xg.data_ptr(), C.byref(ms), 1)
+            assert rc == 0, f"cuFFT reference failed ({rc})"
+            del xg
+            for r in range(world):
+                sz, st0 = dfft.layout(decomp, trn, *shp, p1, p2, r, 3)
+                if r == 0:
+                    blk = out[:n_out].reshape(osz)
+                else:
+                    blk = torch.empty(sz, dtype=cdt, device="cuda")
+                    dist.recv(torch.view_as_real(blk), src=r)
+                rblk = ref[st0[0]:st0[0] + sz[0], st0[1]:st0[1] + sz[1], st0[2]:st0[2] + sz[2]]
+                step = max(1, (1 << 24) // (sz[1] * sz[2]))
+                for a in range(0, sz[0], step):
+                    d = blk[a:a + step] - rblk[a:a + step]
+                    worst[0] += (d.real.double() ** 2 + d.imag.double() ** 2).sum()
+                    worst[1] += (rblk[a:a + step].real.double() ** 2 + rblk[a:a + step].imag.double() ** 2).sum()
+                del blk
+            del ref
+        else:
+            dist.send(torch.view_as_real(out[:n_out].reshape(osz).contiguous()), dst=0)
+        dist.broadcast(worst, src=0)
+        rel = float((worst[0] / worst[1]).sqrt())
+        ok = rel < tol
+        fails += 0 if ok else 1
+        if rank == 0:
+            print(f"{'ok  ' if ok else 'FAIL'} full-size vs cuFFT 3D: {name} {shp}: rel L2 {rel:.2e} (tol {tol:g})", flush=True)
+        del x, out
+        plan.destroy()
+        torch.cuda.empty_cache()
+    return fails
+
+
+def work_area_inside_allocation(comm, rank, world):
+    """setWorkArea with a caller-owned arena that is NOT the base of its allocation (a slice of a caching-allocator
+    tensor), Peer2Peer over > 1 ranks: peers must add the arena's offset inside the IPC-exported allocation."""
+    shape = (64, 64, 64)
+    fails = 0
+    for cls, grid in ((dfft.MPIcuFFT_Slab, None), (dfft.MPIcuFFT_Pencil, (1, world))):
+        plan = cls(dfft.Configurations(), comm, precision="double", transform="r2c")
+        plan.initFFT(dfft.GlobalSize(*shape), dfft.Pencil_Partition(*grid) if grid else None, False)
+        need = plan.getWorkSizeDevice()
+        off = 1 << 20  # 1 MiB into the tensor (keeps 256-byte alignment), different garbage in front on every rank
+        big = torch.full((need + off + 4096,), 0x5A, dtype=torch.uint8, device="cuda")
+        guard = big[:off].clone()
+        plan.setWorkArea(big[off:])
+        isz, ist, osz, ost = plan.getInSize(), plan.getInStart(), plan.getOutSize(), plan.getOutStart()
+        xg = O.real_input(shape)
+        ref = O.fft_r2c(xg)
+        xin = torch.from_numpy(np.ascontiguousarray(O.block(xg, ist, isz))).cuda()
+        out = torch.empty(plan.getDomainSize() // 16, dtype=torch.complex128, device="cuda")
+        errs = []
+        for _ in range(2):
+            plan.execR2C(out, xin)
+            n_out = osz[0] * osz[1] * osz[2]
+            errs.append(O.rel_l2(out[:n_out].cpu().numpy().reshape(osz), O.block(ref, ost, osz)))
+        intact = bool(torch.equal(big[:off], guard))
+        e = torch.tensor([max(errs), 0.0 if intact else 1.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        ok = float(e[0]) < 1e-10 and float(e[1]) == 0.0
+        fails += 0 if ok else 1
+        if rank == 0:
+            print(f"{'ok  ' if ok else 'FAIL'} setWorkArea(arena at +1 MiB inside a tensor) {cls.__name__}: fwd={float(e[0]):.2e} guard intact={float(e[1]) == 0.0}", flush=True)
+        plan.destroy()
+        del big
+    return fails
+
+
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     comm = dfft.Comm.from_torch_distributed(local)
+    if "--cufft" in sys.argv:
+        fails = full_size_vs_cufft(comm, rank, world)
+        if rank == 0:
+            print(f"mgpu_parity --cufft: {fails} failed", flush=True)
+        dist.destroy_process_group()
+        sys.exit(1 if fails else 0)
     if "--full" in sys.argv:
         fails = full_size_properties(comm, rank, world)
         if rank == 0:
@@ -97,14 +245,21 @@ def main():
         for transform in (dfft.R2C, dfft.C2C):
             for shape in ([(32, 16, 64)] if quick else [(32, 16, 64), (64, 64, 256), (16, 128, 8), (256, 64, 128)]):
                 cases.append((dfft.MPIcuFFT_Slab, "streams", dfft.CommunicationMethod.Peer2Peer, prec, transform, shape))
-    fails = 0
+    # overlapped pencil schedule (both send methods Streams), blocked hand-over needs >= 4 block widths of z per rank
+    for transform in (dfft.R2C, dfft.C2C):
+        for g in grids:
+            cases.append((dfft.MPIcuFFT_Pencil, ("streams",) + g, dfft.CommunicationMethod.Peer2Peer, dfft.F64, transform, (16, 32, 1024 * (world // 2 if world > 2 else 1))))
+            if not quick:
+                cases.append((dfft.MPIcuFFT_Pencil, g, dfft.CommunicationMethod.Peer2Peer, dfft.F32, transform, (32, 16, 2048)))
+    fails = work_area_inside_allocation(comm, rank, world)
     for cls, grid, method, prec, transform, shape in cases:
-        streams = grid == "streams"
+        streams = grid == "streams" or (isinstance(grid, tuple) and grid[0] == "streams")
         if streams:
-            grid = None
+            grid = None if grid == "streams" else grid[1:]
         f64 = prec == dfft.F64
         tol = 1e-10 if f64 else 1e-5
-        cfg = dfft.Configurations(comm_method=method, comm_method2=method, send_method=dfft.SendMethod.Streams if streams else dfft.SendMethod.Sync)
+        snd = dfft.SendMethod.Streams if streams else dfft.SendMethod.Sync
+        cfg = dfft.Configurations(comm_method=method, comm_method2=method, send_method=snd, send_method2=snd)
         plan = cls(cfg, comm, precision="double" if f64 else "float", transform="c2c" if transform == dfft.C2C else "r2c")
         part = dfft.Pencil_Partition(*grid) if grid else None
         plan.initFFT(dfft.GlobalSize(*shape), part, True)

@@ -74,6 +74,8 @@ def _fake_dfft():
     m.MPIcuFFT_Slab = m.MPIcuFFT_Slab_Z_Then_YX = m.MPIcuFFT_Pencil = Plan
     m.Pencil_Partition = lambda a, b: (a, b)
     m.HostExecutor = HostExecutor
+    m.pinned_empty = lambda n, dtype, device=None: torch.empty(n, dtype=dtype)
+    m.gpu_local_cpus = lambda device: None
     m.FORWARD, m.INVERSE = -1, 1
     return m
 
@@ -114,7 +116,7 @@ def test_bench_single_gpu_flow_with_mocks(monkeypatch, capsys, extra):
     import importlib
     bench = importlib.import_module("bench")
     monkeypatch.setattr(bench, "ClockSampler", lambda idx: types.SimpleNamespace(stop=lambda: {"sm_mhz": 1900.0, "sm_max_mhz": 1965.0, "reasons": []}))
-    monkeypatch.setattr(bench, "cpu_fft_sample", lambda shape, reps=1: (0.5, 8, "mock sample"))
+    monkeypatch.setattr(bench, "cpu_fft_sample", lambda shape, reps=1, cores=None: (0.5, 8, "mock sample", 7.5))
     monkeypatch.setattr(os.path, "exists", lambda p, _e=os.path.exists: False if p.endswith("libcufft_ref.so") else _e(p))
     if world > 1:
         # per-step labels of a multi-rank slab / pencil plan
@@ -123,7 +125,7 @@ def test_bench_single_gpu_flow_with_mocks(monkeypatch, capsys, extra):
             steps = [("z pass", 0.6), ("y pass", 1.0), ("nccl all-to-all", 3.2), ("x pass", 0.9)]
         monkeypatch.setattr(sys.modules["distributedfft_b200"].MPIcuFFT_Slab, "stepTimes", lambda self: steps)
         monkeypatch.setattr(sys.modules["distributedfft_b200"].MPIcuFFT_Slab, "lastBreakdown", lambda self: {"fft_ms": 4.2, "exchange_ms": 0.03, "total_ms": 4.3})
-    bench.main(["--gpus", str(world), "--steps", "4", "--warmup", "3", "--shape", "32,32,32", *extra])
+    bench.main(["--gpus", str(world), "--steps", "4", "--warmup", "3", "--shape", "32,32,32", "--no-parity", *extra])
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
                 "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):

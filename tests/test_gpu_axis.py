@@ -70,7 +70,7 @@ def test_strided_c2c(prec, a, n, b):
     assert O.rel_l2(host(buf), np.fft.fft(x.astype(np.complex128), axis=1)) < TOL[prec]
 
 
-@pytest.mark.parametrize("env", [{"DFFT_WIDE_TILES": "1"}, {"DFFT_PIPE": "1"}, {"DFFT_PIPE": "1", "DFFT_WIDE_TILES": "1"}, {"DFFT_WIDE_TILES": "-1"}])
+@pytest.mark.parametrize("env", [{"DFFT_WIDE_TILES": "1"}, {"DFFT_WIDE_TILES": "-1"}])
 def test_kernel_variants(env, monkeypatch):
     """The alternative kernel variants (wide tiles, persistent register-prefetch) are selected by environment
     variables that the launcher reads at every launch."""

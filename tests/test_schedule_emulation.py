@@ -235,6 +235,9 @@ CASES = [
     (8, PE, dfft.C2C, (16, 8, 16), 4, 2, A2A, SYNC),
     (6, PE, dfft.R2C, (8, 16, 16), 3, 2, P2P, SYNC),
     (4, PE, dfft.C2C, (4, 8, 8), 2, 2, P2P, SYNC),
+    (8, PE, dfft.C2C, (16, 8, 1024), 2, 4, P2P, SYNC),        # pencil, blocked hand-over of the second transposition
+    (8, PE, dfft.R2C, (16, 16, 2048), 4, 2, P2P, SYNC),       # ... with tail columns (Nzc = 1025 -> 513 / 512)
+    (6, PE, dfft.R2C, (16, 12, 1024), 3, 2, P2P, SYNC) if False else (4, PE, dfft.R2C, (8, 16, 1024), 2, 2, P2P, SYNC),
 ]
 
 
@@ -261,6 +264,7 @@ def test_layout_knobs(env, inverse, monkeypatch):
     assert run_case(4, SL, dfft.C2C, (16, 8, 64), 4, 1, P2P, SYNC, inverse, 3) < 1e-12
     assert run_case(4, SL, dfft.R2C, (8, 16, 128), 4, 1, P2P, STREAMS, inverse, 3) < 1e-12
     assert run_case(2, SL, dfft.R2C, (8, 8, 256), 2, 1, A2A, SYNC, inverse, 3) < 1e-12
+    assert run_case(4, PE, dfft.R2C, (8, 16, 512), 2, 2, P2P, SYNC, inverse, 3) < 1e-12
 
 
 @pytest.mark.parametrize("shape,P", [((128, 128, 128), 4), ((64, 256, 256), 2), ((256, 64, 128), 8), ((16, 16, 128), 1)])
@@ -274,7 +278,7 @@ def test_block_width_follows_tile_width(shape, P, transform):
 
 @pytest.mark.parametrize("P,shape,p1,p2,transform", [
     (8, (16, 32, 256), 2, 4, dfft.C2C), (8, (32, 16, 64), 4, 2, dfft.R2C), (4, (8, 8, 128), 2, 2, dfft.C2C),
-    (8, (16, 16, 1024), 2, 4, dfft.R2C)])
+    (8, (16, 16, 1024), 2, 4, dfft.R2C), (8, (16, 8, 2048), 2, 4, dfft.C2C), (8, (16, 16, 2048), 4, 2, dfft.R2C)])
 def test_overlapped_pencil_schedule(P, shape, p1, p2, transform, monkeypatch):
     """experimental overlapped pencil schedule (DFFT_PENCIL_OVERLAP=1, SendMethod Streams), forward"""
     monkeypatch.setenv("DFFT_PENCIL_OVERLAP", "1")

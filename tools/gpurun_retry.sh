@@ -1,10 +1,9 @@
 #!/bin/bash
-# gpurun with retries while the pod is busy (exit code 3 = nothing charged).  Usage: gpurun_retry.sh <log> <gpurun args...>
-LOG=$1; shift
+# usage: tools/gpurun_retry.sh <logfile> <gpurun args...>   — retries while the pod answers "transient" (nothing charged)
+log=$1; shift
 for i in $(seq 1 40); do
-  /usr/local/graft/bin/gpurun "$@" > "$LOG" 2>&1
-  rc=$?
-  if [ $rc -ne 3 ]; then exit $rc; fi
-  sleep 45
+  /usr/local/graft/bin/gpurun "$@" > "$log" 2>&1
+  if grep -q "status=transient" "$log" || grep -q "retry in a few minutes" "$log"; then sleep 90; continue; fi
+  break
 done
-exit 3
+tail -100 "$log"

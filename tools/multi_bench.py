@@ -39,11 +39,13 @@ def main():
                 import json
                 d = json.loads(line)
                 r = d["roofline"]
-                print(name, "ms", round(d["ms_per_step"], 3), "GFLOP/s", round(d["value"]), "seq_ms", round(d["config"]["sequential_schedule_ms"], 3),
+                par = d["config"].get("parity") or {}
+                print(name, "ms", round(d["ms_per_step"], 3), "inv_ms", round(d["config"]["ms_inverse"], 3), "GFLOP/s", round(d["value"]), "seq_ms", round(d["config"]["sequential_schedule_ms"], 3),
+                      "parity", par.get("ok"), (par.get("small_grid") or {}).get("rel_l2_forward_max_over_ranks"),
                       "steps", {k: round(v, 3) for k, v in r["steps_ms"].items()}, "nvlink", [x.get("gbs_per_direction") for x in (r["nvlink"] if isinstance(r.get("nvlink"), list) else [r.get("nvlink", {})])], flush=True)
-        except Exception as ex:  # keep going: the box is expensive
+        except (Exception, SystemExit) as ex:  # keep going: the box is expensive
             if rank == 0:
-                print(name, "FAILED", repr(ex), flush=True)
+                print(name, "FAILED", repr(ex), buf.getvalue()[-600:], flush=True)
         for e in envs:
             os.environ.pop(e.split("=", 1)[0], None)
     if world > 1:
