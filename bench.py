@@ -471,6 +471,19 @@ def main(argv=None):
     seq_ms = bd_acc["total_ms"] / reps
     if bplan is not plan:
         bplan.destroy()
+    timeline = None
+    if send == "Streams" and hasattr(plan, "timeline"):
+        # where every step of the overlapped schedule ran (stream, begin, end) — rank 0's view of one exec
+        plan.enableTimer(True)
+        for _ in range(2):
+            barrier()
+            step()
+            plan.wait()
+        try:
+            timeline = [{"step": l, "stream": st_, "begin_ms": round(b0, 4), "end_ms": round(e0, 4)} for l, st_, b0, e0 in plan.timeline()]
+        except Exception:
+            timeline = None
+        plan.enableTimer(False)
     labels = [n for n, _ in st]
     step_ms = [a / reps for a in acc_steps]
     names = [n for n, _ in pt]
@@ -500,7 +513,7 @@ def main(argv=None):
                 "peak_source": peak_src, "kernel": f"dominant FFT pass: {dom['step']} ({dom['ms']:.3f} ms per launch; algorithmic bytes = one read + one write of the local array)",
                 "all_passes": passes, "all_passes_achieved": tot_bytes / (fft_ms * 1e-3) / 1e9, "all_passes_frac": tot_bytes / (fft_ms * 1e-3) / 1e9 / hbm_peak,
                 "fft_ms": fft_ms, "exchange_ms": bd_avg["exchange_ms"], "steps_ms": dict(zip([f"{i}:{l}" for i, l in enumerate(labels)], step_ms)),
-                "phases_cumulative_ms": dict(zip(names, cum))}
+                "phases_cumulative_ms": dict(zip(names, cum)), "overlap_timeline": timeline}
     if world > 1:
         def link(sent, t_x, note):
             return {"bytes_sent_per_gpu": sent, "transfer_ms": t_x, "gbs_per_direction": (sent / (t_x * 1e-3) / 1e9) if t_x else None,

@@ -267,6 +267,7 @@ struct dfft_plan_s {
     std::vector<cudaEvent_t> sync_events;
     cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
     int xchg_ctas = 0;                            // SMs given to the exchange pass in overlapped schedules
+    int ovl_groups = 4, ovl_chunks = 4;           // overlapped schedules: plane groups of the z pass, z chunks of the y / x passes
     int blocked_ch = 0;                           // > 0: slab forward keeps the y->x intermediate as [b/CH][Nx][CH]
     int xchg_tile_pref = 2;                       // tile preference of passes that store into other GPUs (2 = wide rows)
     long long rendezvous_timeout_cycles = 0;      // device clock cycles a rendezvous waits for a peer (0 = forever)
@@ -283,6 +284,11 @@ struct dfft_plan_s {
     std::vector<int> ev_is_fft;  // 1 fft pass, 0 exchange
     std::vector<const char*> ev_labels;
     int n_events_used = 0;
+    // timeline of the last timed exec: one (begin, end) event pair per step, recorded on the step's own stream
+    std::vector<cudaEvent_t> tl_events;
+    std::vector<const char*> tl_labels;
+    std::vector<int> tl_streams;
+    int tl_used = 0;
     int last_launches = 0;
     int execs = 0;
     double init_ms = 0;          // "init" section of the reference's CSV
@@ -856,8 +862,8 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
 
     // plane groups (of my x planes) and z chunks
     Split groups, chunks;
-    const size_t NG = std::min<size_t>(4, nx_p);
-    const size_t NS = nzc >= 128 ? 4 : (nzc >= 32 ? 2 : 1);
+    const size_t NG = std::min<size_t>(size_t(p->ovl_groups), nx_p);
+    const size_t NS = nzc >= 32 * size_t(p->ovl_chunks) ? size_t(p->ovl_chunks) : (nzc >= 32 ? 2 : 1);
     groups.make(nx_p, NG);
     const size_t CH = inverse ? 0 : size_t(p->blocked_ch);
     const size_t rem = CH ? nzc % CH : 0, nzm = nzc - rem;
@@ -1100,8 +1106,8 @@ static int build_overlapped_pencil(dfft_plan_s* p, Schedule& sc) {
     size_t min_nx = nx, min_nz = g.nzc;
     for (size_t v : g.sx.size) min_nx = std::min(min_nx, v);
     for (size_t v : g.sz.size) min_nz = std::min(min_nz, v);
-    const size_t NG = std::min<size_t>(4, min_nx);
-    const size_t NS = min_nz >= 128 ? 4 : (min_nz >= 32 ? 2 : 1);
+    const size_t NG = std::min<size_t>(size_t(p->ovl_groups), min_nx);
+    const size_t NS = min_nz >= 32 * size_t(p->ovl_chunks) ? size_t(p->ovl_chunks) : (min_nz >= 32 ? 2 : 1);
     Split groups, chunks;
     groups.make(nx_i, NG);
     // blocked hand-over of the second transposition: receiver (q, j) holds [nz_j/CH][nx][ny_q][CH] (+ a plain-layout
@@ -1414,9 +1420,25 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
         CK_CUDA(cudaStreamWaitEvent(p->aux[1], p->fork_ev, 0));
     }
     CK_CUDA(mark("start", -1));
+    int tl = 0;
+    auto tl_mark = [&](cudaStream_t ss_, const char* label, int stream_id) -> cudaError_t {
+        if (!timing) return cudaSuccess;
+        if (tl >= int(p->tl_events.size())) {
+            cudaEvent_t e;
+            cudaError_t r = cudaEventCreate(&e);
+            if (r != cudaSuccess) return r;
+            p->tl_events.push_back(e);
+            p->tl_labels.push_back(label);
+            p->tl_streams.push_back(stream_id);
+        }
+        p->tl_labels[tl] = label;
+        p->tl_streams[tl] = stream_id;
+        return cudaEventRecord(p->tl_events[tl++], ss_);
+    };
     for (Step& s : sc.steps) {
         cudaStream_t ss = streams[s.stream];
         for (int w : s.waits) CK_CUDA(cudaStreamWaitEvent(ss, p->sync_events[w], 0));
+        CK_CUDA(tl_mark(ss, s.label, s.stream));
         if (s.type == STEP_PASS) {
             FftParams prm = s.prm;
             // views on the caller's buffers store a byte offset in seg[0].base
@@ -1452,8 +1474,10 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
                     CK_CUDA(cudaMemcpyAsync(rb + s.roff[q] * es, sb + s.soff[q] * es, s.scount[q] * es, cudaMemcpyDeviceToDevice, ss));
             CK_CUDA(mark(s.phase, 0, s.label));
         }
+        CK_CUDA(tl_mark(ss, s.label, s.stream));
         if (s.record >= 0) CK_CUDA(cudaEventRecord(p->sync_events[s.record], ss));
     }
+    if (timing) p->tl_used = tl;
     if (sc.overlapped) {
         for (int a = 0; a < 2; ++a) {
             CK_CUDA(cudaEventRecord(p->join_ev[a], p->aux[a]));
@@ -1517,6 +1541,7 @@ static int exec_common(dfft_plan_t p, void* out, const void* in, int inverse, in
     if (!sync) return DFFT_SUCCESS;
     rc = dfft_plan_wait(p);
     if (rc) return rc;
+    CK_CUDA(cudaDeviceSynchronize());  // the reference's execs end like this (mpicufft_slab.cpp:807, 870)
     // the reference gathers and appends the section times after every non-warm-up exec
     // (mpicufft_slab.cpp:817-821)
     if (!p->csv_path.empty() && p->timing && d == 3) {
@@ -1737,6 +1762,8 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         // NVLink store efficiency grows with the contiguous run per row: 64-byte rows reach 434 GB/s per direction,
         // 128-byte rows 700 GB/s, 2 KB runs 704 GB/s (profiles/r01_8gpu, r01_bench_n2_*): exchanging passes prefer the
         // wide tile even though it is slower as a purely local pass.  DFFT_XCHG_WIDE=0 keeps the narrow tile.
+        if (const char* eg = getenv("DFFT_OVL_GROUPS")) p->ovl_groups = std::max(1, std::min(16, atoi(eg)));
+        if (const char* ec = getenv("DFFT_OVL_CHUNKS")) p->ovl_chunks = std::max(1, std::min(16, atoi(ec)));
         const char* et = getenv("DFFT_RENDEZVOUS_TIMEOUT_S");
         const double tsec = et ? atof(et) : 300.0;
         p->rendezvous_timeout_cycles = tsec > 0 ? (long long)(tsec * 1.9e9) : 0;  // clock64 ticks at <= 1.965 GHz
@@ -1831,6 +1858,7 @@ int dfft_plan_destroy(dfft_plan_t p) {
     if (p->err_d) cudaFree(p->err_d);
     p->tabs.release();
     for (cudaEvent_t e : p->events) cudaEventDestroy(e);
+    for (cudaEvent_t e : p->tl_events) cudaEventDestroy(e);
     for (cudaEvent_t e : p->sync_events) cudaEventDestroy(e);
     if (p->fork_ev) cudaEventDestroy(p->fork_ev);
     for (int a = 0; a < 2; ++a) {
@@ -1986,6 +2014,28 @@ int dfft_get_step_times(dfft_plan_t p, double* ms, int capacity) {
         ms[n] = f;
     }
     return n;
+}
+// Timeline of the last timed exec: step i ran on plan stream `stream[i]` (0 caller's, 1 exchange, 2 follow-up) from
+// begin_ms[i] to end_ms[i] after the start of the exec.  The way to look at an overlapped (Streams) schedule.
+int dfft_get_timeline(dfft_plan_t p, double* begin_ms, double* end_ms, int* stream, int capacity) {
+    if (!p) return fail(DFFT_ERR_INVALID, "null plan");
+    if (p->n_events_used < 2 || p->tl_used < 2) return fail(DFFT_ERR_STATE, "no timed exec yet (dfft_timer_enable)");
+    CK_CUDA(cudaEventSynchronize(p->events[p->n_events_used - 1]));
+    const int n = p->tl_used / 2;
+    for (int i = 0; i < n && i < capacity; ++i) {
+        float a = 0, b = 0;
+        CK_CUDA(cudaEventSynchronize(p->tl_events[2 * i + 1]));
+        CK_CUDA(cudaEventElapsedTime(&a, p->events[0], p->tl_events[2 * i]));
+        CK_CUDA(cudaEventElapsedTime(&b, p->events[0], p->tl_events[2 * i + 1]));
+        if (begin_ms) begin_ms[i] = a;
+        if (end_ms) end_ms[i] = b;
+        if (stream) stream[i] = p->tl_streams[2 * i];
+    }
+    return n;
+}
+const char* dfft_get_timeline_label(dfft_plan_t p, int i) {
+    if (!p || i < 0 || 2 * i >= p->tl_used) return nullptr;
+    return p->tl_labels[2 * i];
 }
 // JSON description of a schedule (test hook: tests/test_schedule_emulation.py replays it with numpy)
 static void json_view(std::string& o, const View& v, const Tables& T) {

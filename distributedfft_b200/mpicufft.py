@@ -210,6 +210,13 @@ class MPIcuFFT:
         n = check(lib().dfft_get_step_times(self._h, ms, n))
         return [(lib().dfft_get_step_label(self._h, i).decode(), float(ms[i])) for i in range(n)]
 
+    def timeline(self):
+        """[(label, stream, begin_ms, end_ms)] of the last timed exec — every step on its own plan stream."""
+        cap = 256
+        b = (C.c_double * cap)(); e = (C.c_double * cap)(); st = (C.c_int * cap)()
+        n = check(lib().dfft_get_timeline(self._h, b, e, st, cap))
+        return [(lib().dfft_get_timeline_label(self._h, i).decode(), int(st[i]), float(b[i]), float(e[i])) for i in range(min(n, cap))]
+
     def lastBreakdown(self):
         f, x, t = C.c_double(), C.c_double(), C.c_double()
         check(lib().dfft_get_last_breakdown(self._h, C.byref(f), C.byref(x), C.byref(t)))

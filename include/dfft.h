@@ -162,6 +162,11 @@ int dfft_get_phase_times(dfft_plan_t plan, double* ms, int capacity);
 int dfft_get_step_count(dfft_plan_t plan);
 const char* dfft_get_step_label(dfft_plan_t plan, int i);
 int dfft_get_step_times(dfft_plan_t plan, double* ms, int capacity);
+/* Timeline of the last timed exec (also for overlapped schedules, whose steps run on three streams): step i ran on
+ * plan stream stream[i] (0 the caller's, 1 exchange, 2 follow-up) from begin_ms[i] to end_ms[i] after the exec's start.
+ * Returns the number of steps. */
+int dfft_get_timeline(dfft_plan_t plan, double* begin_ms, double* end_ms, int* stream, int capacity);
+const char* dfft_get_timeline_label(dfft_plan_t plan, int i);
 /* Collective: gathers the section times of the last timed exec to rank 0, which appends one block to the CSV
  * in the reference's schema (src/timer.cpp:58-101).  Called automatically after every non-warm-up
  * synchronous exec when Configurations::benchmark_dir is set. */
