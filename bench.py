@@ -538,9 +538,9 @@ def main(argv=None):
     if rank == 0 and world == 1:
         if not args.no_cpu:
             cs = bounded_cpu_shape(shape)
-            sec, cores, desc, par = cpu_fft_sample(cs, reps=1)
+            sec, cores, desc, eff_par = cpu_fft_sample(cs, reps=1)
             cpu = {"value": flops_c2c(cs) / sec / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": desc, "ms": sec * 1e3,
-                   "threads_effective": par}
+                   "threads_effective": eff_par}
         ref = os.path.join(ROOT, "oracle", "_ref", "libcufft_ref.so")
         if os.path.exists(ref) and c2c:
             try:

@@ -269,6 +269,7 @@ struct dfft_plan_s {
     int xchg_ctas = 0;                            // SMs given to the exchange pass in overlapped schedules
     int ovl_groups = 4, ovl_chunks = 4;           // overlapped schedules: plane groups of the z pass, z chunks of the y / x passes
     int blocked_ch = 0;                           // > 0: slab forward keeps the y->x intermediate as [b/CH][Nx][CH]
+    int blocked_inv = 1;                          // the inverse x -> y hand-over is blocked as well (DFFT_BLOCKED_INV=0: plain)
     int xchg_tile_pref = 2;                       // tile preference of passes that store into other GPUs (2 = wide rows)
     long long rendezvous_timeout_cycles = 0;      // device clock cycles a rendezvous waits for a peer (0 = forever)
     int bulk_store = 0;                           // experimental: exchanging y pass stores with cp.async.bulk (DFFT_BULK_STORE=1)
@@ -719,6 +720,91 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
 
     // pencil / slab zy_x inverse
     const bool slab = g.decomp == DFFT_SLAB_ZY_THEN_X;
+    // Blocked hand-over for the inverse as well (mirror of the forward one): the x pass stores into the receivers as
+    // [nz_j/CH][ny][nx_q][CH] (+ a plain tail of nz_j % CH columns), so the rows a tile sends to one destination —
+    // consecutive x — are adjacent (one contiguous run per destination), and the y pass reads rows nx_i*CH apart
+    // instead of one row per (y, z) plane.  DFFT_BLOCKED_INV=0 keeps the plain layout.
+    const size_t CHI = (d == 3 && dir2 && dir1 && p->blocked_inv) ? size_t(p->blocked_ch) : 0;
+    if (CHI) {
+        const size_t CH = CHI;
+        const size_t rem = nz_j % CH, nzm = nz_j - rem;
+        bool any_rem = false;
+        if (g.decomp == DFFT_PENCIL) { for (size_t v : g.sz.size) any_rem = any_rem || (v % CH != 0); }
+        else any_rem = rem != 0;
+        // x pass: in = caller's [nx][oy_i][nz_j]; tile = (y_loc, z block); n = x
+        Step s3;
+        rc = new_pass(PASS_C2C_TILED, g.nx, "1D FFT X-Direction", s3);
+        if (rc) return rc;
+        s3.label = "x pass";
+        s3.prm.A0 = int(oy_i); s3.prm.A1 = int(nzm / CH); s3.prm.B = int(CH);
+        s3.prm.in = single_view(nullptr, (long long)nz_j, (long long)CH, (long long)(oy_i * nz_j));
+        s3.in_user = 1;
+        s3.prm.tile_pref = G2.size() > 1 ? p->xchg_tile_pref : 1;
+        s3.prm.bulk_out = G2.size() > 1 ? p->bulk_store : 0;
+        seg_view(s3.prm.out, tab_x, G2, [&](int q, int r) {
+            const size_t nxq = g.sx.size[q];
+            return mkseg(eptr(slotp(D2, r), oy0_i * nxq * CH, es), (long long)(nxq * CH), (long long)(g.ny * nxq * CH), (long long)CH, g.sx.start[q]);
+        });
+        Step s3t;
+        if (any_rem) {  // leftover columns: plain [nx_q][ny][rem] behind the blocked part
+            s3t = s3;
+            s3t.label = "x pass (tail)";
+            s3t.phase = nullptr;
+            s3t.prm.bulk_out = 0;
+            s3t.prm.A0 = int(oy_i); s3t.prm.A1 = 1; s3t.prm.B = int(rem);
+            s3t.prm.in = single_view((void*)(size_t)(nzm * es), (long long)nz_j, 0, (long long)(oy_i * nz_j));
+            seg_view(s3t.prm.out, tab_x, G2, [&](int q, int r) {
+                const size_t nxq = g.sx.size[q];
+                return mkseg(eptr(slotp(D2, r), g.ny * nxq * nzm + oy0_i * rem, es), (long long)rem, 0, (long long)(g.ny * rem), g.sx.start[q]);
+            });
+            const char* ph = s3.phase; s3.phase = nullptr; s3t.phase = ph;
+            sc.steps.push_back(s3);
+            sc.steps.push_back(s3t);
+        } else {
+            sc.steps.push_back(s3);
+        }
+        if (G2.size() > 1) rendezvous(2, 2, slab ? "Transpose (Finished Receive)" : "Second Transpose (Finished Receive)");
+        // y pass: in = my slot, blocked [nz_j/CH][ny][nx_i][CH]; tile = (x_loc, z block); n = y
+        Step s2;
+        rc = new_pass(PASS_C2C_TILED, g.ny, slab ? nullptr : "1D FFT Y-Direction", s2);
+        if (rc) return rc;
+        s2.label = "y pass";
+        s2.prm.A0 = int(nx_i); s2.prm.A1 = int(nzm / CH); s2.prm.B = int(CH);
+        s2.prm.in = single_view(slotp(D2, me), (long long)CH, (long long)(g.ny * nx_i * CH), (long long)(nx_i * CH));
+        if (G1.size() > 1) s2.prm.tile_pref = p->xchg_tile_pref;
+        else s2.prm.tile_pref = 1;
+        seg_view(s2.prm.out, tab_y_in, G1, [&](int q, int r) {
+            const size_t nyq = g.sy.size[q];
+            return mkseg(eptr(slotp(D1, r), z0_j, es), (long long)(nyq * nzc), (long long)CH, (long long)nzc, g.sy.start[q]);
+        });
+        if (any_rem) {
+            Step s2t = s2;
+            s2t.label = "y pass (tail)";
+            s2t.phase = nullptr;
+            s2t.prm.A0 = int(nx_i); s2t.prm.A1 = 1; s2t.prm.B = int(rem);
+            s2t.prm.in = single_view(eptr(slotp(D2, me), g.ny * nx_i * nzm, es), (long long)(g.ny * rem), 0, (long long)rem);
+            seg_view(s2t.prm.out, tab_y_in, G1, [&](int q, int r) {
+                const size_t nyq = g.sy.size[q];
+                return mkseg(eptr(slotp(D1, r), z0_j + nzm, es), (long long)(nyq * nzc), 0, (long long)nzc, g.sy.start[q]);
+            });
+            const char* ph = s2.phase; s2.phase = nullptr; s2t.phase = ph;
+            sc.steps.push_back(s2);
+            sc.steps.push_back(s2t);
+        } else {
+            sc.steps.push_back(s2);
+        }
+        if (G1.size() > 1) rendezvous(1, 1, "First Transpose (Finished Receive)");
+        Step s1;
+        rc = new_pass(zkind, zlen, slab ? "2D FFT Y-Z-Direction" : "1D FFT Z-Direction", s1);
+        if (rc) return rc;
+        s1.prm.A0 = int(nx_i); s1.prm.A1 = int(ny_j);
+        s1.prm.in = single_view(slotp(D1, me), (long long)(ny_j * nzc), (long long)nzc, 1);
+        s1.prm.out = single_view(nullptr, zpitch_out * (long long)ny_j, zpitch_out, 1);
+        s1.out_user = 2;
+        sc.steps.push_back(s1);
+        sc.built = true;
+        return DFFT_SUCCESS;
+    }
     Step x2;
     bool have_in_slot = false;  // whether the y pass input is in a slot (d == 3) or the caller's buffer (d == 2)
     if (d == 3) {
@@ -865,7 +951,7 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
     const size_t NG = std::min<size_t>(size_t(p->ovl_groups), nx_p);
     const size_t NS = nzc >= 32 * size_t(p->ovl_chunks) ? size_t(p->ovl_chunks) : (nzc >= 32 ? 2 : 1);
     groups.make(nx_p, NG);
-    const size_t CH = inverse ? 0 : size_t(p->blocked_ch);
+    const size_t CH = (inverse && !p->blocked_inv) ? 0 : size_t(p->blocked_ch);  // blocked hand-over, both directions
     const size_t rem = CH ? nzc % CH : 0, nzm = nzc - rem;
     if (CH) {  // z chunks are whole multiples of the block width; the Nzc % CH leftover columns ride with the last chunk
         Split u;
@@ -983,27 +1069,54 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
             }
         }
     } else {
-        std::vector<int> ev_x(NS), ev_yi(NS);
-        for (size_t c = 0; c < NS; ++c) {
+        std::vector<int> ev_x(NSc), ev_yi(NSc);
+        for (size_t c = 0; c < NSc; ++c) {
             const size_t z0 = chunks.start[c], zc = chunks.size[c];
             Step s;
             rc = new_pass(PASS_C2C_TILED, nx, "x pass", s);
             if (rc) return rc;
-            s.prm.A0 = 1; s.prm.A1 = int(oy_me); s.prm.B = int(zc);
-            s.prm.in = single_view((void*)(size_t)(z0 * es), 0, (long long)nzc, (long long)(oy_me * nzc));
             s.in_user = 1;
-            // dest q holds [nx_q][ny][nzc]; my rows y in [oy0_me, +oy_me)
-            seg_view(s.prm.out, tab_x, G2, [&](int q, int r) {
-                return mkseg(eptr(slotp(D2, r), oy0_me * nzc + z0, es), 0, (long long)nzc, (long long)(ny * nzc), g.sx.start[q]);
-            });
+            if (CH) {
+                // dest q holds [nzc/CH][ny][nx_q][CH]: the rows a tile sends to one destination (consecutive x) are adjacent
+                s.prm.A0 = int(oy_me); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
+                s.prm.in = single_view((void*)(size_t)(z0 * es), (long long)nzc, (long long)CH, (long long)(oy_me * nzc));
+                s.prm.bulk_out = p->bulk_store;
+                seg_view(s.prm.out, tab_x, G2, [&](int q, int r) {
+                    const size_t nxq = g.sx.size[q];
+                    return mkseg(eptr(slotp(D2, r), ((z0 / CH) * ny + oy0_me) * nxq * CH, es), (long long)(nxq * CH), (long long)(ny * nxq * CH), (long long)CH,
+                                 g.sx.start[q]);
+                });
+            } else {
+                s.prm.A0 = 1; s.prm.A1 = int(oy_me); s.prm.B = int(zc);
+                s.prm.in = single_view((void*)(size_t)(z0 * es), 0, (long long)nzc, (long long)(oy_me * nzc));
+                // dest q holds [nx_q][ny][nzc]; my rows y in [oy0_me, +oy_me)
+                seg_view(s.prm.out, tab_x, G2, [&](int q, int r) {
+                    return mkseg(eptr(slotp(D2, r), oy0_me * nzc + z0, es), 0, (long long)nzc, (long long)(ny * nzc), g.sx.start[q]);
+                });
+            }
             s.prm.max_ctas = p->xchg_ctas;
             s.prm.tile_pref = p->xchg_tile_pref;
             s.stream = 1;
             if (c == 0) s.waits.push_back(ev_entry);
-            s.record = ev_x[c] = nev++;
+            const bool tail_here = CH && rem && c + 1 == NSc;
+            if (!tail_here) s.record = ev_x[c] = nev++;
             sc.steps.push_back(s);
+            if (tail_here) {
+                Step t = s;
+                t.label = "x pass (tail)";
+                t.prm.bulk_out = 0;
+                t.waits.clear();
+                t.prm.A0 = int(oy_me); t.prm.A1 = 1; t.prm.B = int(rem);
+                t.prm.in = single_view((void*)(size_t)(nzm * es), (long long)nzc, 0, (long long)(oy_me * nzc));
+                seg_view(t.prm.out, tab_x, G2, [&](int q, int r) {
+                    const size_t nxq = g.sx.size[q];
+                    return mkseg(eptr(slotp(D2, r), ny * nxq * nzm + oy0_me * rem, es), (long long)rem, 0, (long long)(ny * rem), g.sx.start[q]);
+                });
+                t.record = ev_x[c] = nev++;
+                sc.steps.push_back(t);
+            }
         }
-        for (size_t c = 0; c < NS; ++c) {
+        for (size_t c = 0; c < NSc; ++c) {
             const size_t z0 = chunks.start[c], zc = chunks.size[c];
             Step r = rendezvous(2, 2, 2);
             r.waits.push_back(ev_x[c]);
@@ -1011,12 +1124,31 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
             Step s;
             rc = new_pass(PASS_C2C_TILED, ny, "y pass", s);
             if (rc) return rc;
-            s.prm.A0 = int(nx_p); s.prm.A1 = 1; s.prm.B = int(zc);
-            s.prm.in = single_view(eptr(slotp(D2, me), z0, es), (long long)(ny * nzc), 0, (long long)nzc);
-            s.prm.out = s.prm.in;  // in place
             s.stream = 2;
-            s.record = ev_yi[c] = nev++;
-            sc.steps.push_back(s);
+            if (CH) {
+                s.prm.A0 = int(nx_p); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
+                s.prm.tile_pref = 1;
+                s.prm.in = single_view(eptr(slotp(D2, me), (z0 / CH) * ny * nx_p * CH, es), (long long)CH, (long long)(ny * nx_p * CH), (long long)(nx_p * CH));
+                s.prm.out = single_view(eptr(slotp(D1, me), z0, es), (long long)(ny * nzc), (long long)CH, (long long)nzc);
+                const bool tail_here = rem && c + 1 == NSc;
+                if (!tail_here) s.record = ev_yi[c] = nev++;
+                sc.steps.push_back(s);
+                if (tail_here) {
+                    Step t = s;
+                    t.label = "y pass (tail)";
+                    t.prm.A0 = int(nx_p); t.prm.A1 = 1; t.prm.B = int(rem);
+                    t.prm.in = single_view(eptr(slotp(D2, me), ny * nx_p * nzm, es), (long long)(ny * rem), 0, (long long)rem);
+                    t.prm.out = single_view(eptr(slotp(D1, me), nzm, es), (long long)(ny * nzc), 0, (long long)nzc);
+                    t.record = ev_yi[c] = nev++;
+                    sc.steps.push_back(t);
+                }
+            } else {
+                s.prm.A0 = int(nx_p); s.prm.A1 = 1; s.prm.B = int(zc);
+                s.prm.in = single_view(eptr(slotp(D2, me), z0, es), (long long)(ny * nzc), 0, (long long)nzc);
+                s.prm.out = s.prm.in;  // in place
+                s.record = ev_yi[c] = nev++;
+                sc.steps.push_back(s);
+            }
         }
         Step s;
         const PassKind zkind = c2c ? PASS_C2C_CONTIG : PASS_C2R;
@@ -1024,11 +1156,11 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
         rc = new_pass(zkind, c2c ? g.nz : g.nz / 2, c2c ? "z pass" : "z pass (C2R)", s);
         if (rc) return rc;
         s.prm.A0 = int(nx_p); s.prm.A1 = int(ny);
-        s.prm.in = single_view(slotp(D2, me), (long long)(ny * nzc), (long long)nzc, 1);
+        s.prm.in = single_view(slotp(CH ? D1 : D2, me), (long long)(ny * nzc), (long long)nzc, 1);
         s.prm.out = single_view(nullptr, zpitch * (long long)ny, zpitch, 1);
         s.out_user = 2;
         s.stream = 0;
-        for (size_t c = 0; c < NS; ++c) s.waits.push_back(ev_yi[c]);
+        for (size_t c = 0; c < NSc; ++c) s.waits.push_back(ev_yi[c]);
         sc.steps.push_back(s);
     }
     sc.nevents = nev;
@@ -1771,6 +1903,7 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         p->bulk_store = (ebs && atoi(ebs) != 0) ? 1 : 0;
         const char* ew = getenv("DFFT_XCHG_WIDE");
         p->xchg_tile_pref = (ew && atoi(ew) == 0) ? 1 : 2;
+        if (const char* ebi = getenv("DFFT_BLOCKED_INV")) p->blocked_inv = atoi(ebi) != 0;
         const char* eb = getenv("DFFT_BLOCKED");
         // block width = the widest tile the y and x passes use for these lengths (fft_kernels.cuh: Shape::TBT —
         // 4096 points per tile, rows of at least 64 bytes, at most 32 columns), never below 8 elements

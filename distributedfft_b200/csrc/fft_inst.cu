@@ -16,6 +16,54 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);  // read per launch (cheap) so that one process can compare variants
+    return e ? atoi(e) : dflt;
+}
+
+// cuTensorMapEncodeTiled through the runtime (libdfft.so does not link libcuda)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn encode_tiled() {
+    static encode_tiled_fn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) { cudaGetLastError(); f = nullptr; }
+        return (encode_tiled_fn)f;
+    }();
+    return fn;
+}
+
+// rank-4 tensor map (b, n, a1, a0) of a single-segment view; box TB x min(N, 256) x 1 x 1.  false: the view does not
+// meet the TMA constraints (16-byte aligned base and strides) and the register-fed kernel is used instead.
+template <typename T>
+static bool make_view_map(const View& v, int A0, int A1, int N, int B, int TB, CUtensorMap* tm) {
+    encode_tiled_fn enc = encode_tiled();
+    if (!enc || v.nseg != 1) return false;
+    const unsigned long long es = sizeof(cx<T>);
+    const int d0 = sizeof(T) == 8 ? 2 : 1;  // 8-byte units per complex element
+    char* base = reinterpret_cast<char*>(v.seg[0].base) - (long long)v.seg[0].n0 * v.sN * (long long)es;
+    if (reinterpret_cast<unsigned long long>(base) % 16) return false;
+    if (v.sN <= 0 || v.seg[0].sA0 < 0 || v.seg[0].sA1 < 0) return false;
+    cuuint64_t dims[4] = {cuuint64_t(B) * d0, cuuint64_t(N), cuuint64_t(A1 > 0 ? A1 : 1), cuuint64_t(A0 > 0 ? A0 : 1)};
+    unsigned long long sn = (unsigned long long)v.sN * es;
+    unsigned long long s1 = A1 > 1 ? (unsigned long long)v.seg[0].sA1 * es : sn * N;
+    unsigned long long s0 = A0 > 1 ? (unsigned long long)v.seg[0].sA0 * es : sn * N;
+    if (s1 == 0) s1 = sn * N;
+    if (s0 == 0) s0 = sn * N;
+    cuuint64_t strides[3] = {sn, s1, s0};
+    for (int i = 0; i < 3; ++i)
+        if (strides[i] % 16 || strides[i] >= (1ull << 40)) return false;
+    if ((cuuint64_t(TB) * d0 * 8) % 16) return false;
+    cuuint32_t box[4] = {cuuint32_t(TB * d0), cuuint32_t(N < 256 ? N : 256), 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const int promo = env_int("DFFT_TMA_L2PROMO", 0);
+    const CUtensorMapL2promotion l2 = promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                      : (promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : (promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE));
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int wide_tiles() {
     const char* e = getenv("DFFT_WIDE_TILES");
     return e ? atoi(e) : 0;
@@ -33,6 +81,36 @@ static cudaError_t launch_tiled(const FftParams& p, cudaStream_t stream, long lo
     if (p.B <= 0) return cudaSuccess;
     const long long grid = lines * ((p.B + TB - 1) / TB);
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    if constexpr (C::NST >= 2 && LOG2N >= 7) {
+        // TMA-fed persistent kernel (fft_c2c_tma_kernel).  Measured on B200 (tools/axis_bench.py, profiles/r02_axis_*):
+        // 1024-point f64 strided passes +11 % (16 KB pitch), +19 % (far rows), +21 % (blocked hand-over); 512-point f64 and
+        // the f32 tiles lose (their register-fed kernels already run at 0.9+ of the copy bandwidth or use one CTA per
+        // SM), so the default (-1) enables it for f64 lines of 1024 points; DFFT_TMA=1 forces it on, 0 off.
+        const int mode = env_int("DFFT_TMA", -1);
+        const bool want = mode > 0 || (mode < 0 && sizeof(T) == 8 && LOG2N == 10);
+        const bool bulk_ok = p.bulk_out && p.out.sN == TB && p.B == TB;
+        alignas(64) CUtensorMap tm;
+        if (want && p.in.nseg == 1 && (!p.bulk_out || bulk_ok) && make_view_map<T>(p.in, p.A0, p.A1, C::N, p.B, TB, &tm)) {
+            auto tf = fft_c2c_tma_kernel<T, LOG2N, LOG2E, TB, false>;
+            auto ti = fft_c2c_tma_kernel<T, LOG2N, LOG2E, TB, true>;
+            static cudaError_t oncet = set_smem(tf, C::SMEM_BYTES) != cudaSuccess ? cudaErrorInvalidValue : set_smem(ti, C::SMEM_BYTES);
+            if (oncet != cudaSuccess) return oncet;
+            static int resident = [&] {
+                int dev = 0, sms = 0, per = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, tf, C::THREADS, C::SMEM_BYTES) != cudaSuccess || per < 1) per = 1;
+                return sms * per;
+            }();
+            long long g = grid < resident ? grid : resident;
+            if (p.max_ctas > 0 && g > p.max_ctas) g = p.max_ctas;
+            FftParams q = p;
+            q.bulk_out = bulk_ok ? 1 : 0;
+            if (p.inverse) ti<<<unsigned(g), C::THREADS, C::SMEM_BYTES, stream>>>(q, tm);
+            else tf<<<unsigned(g), C::THREADS, C::SMEM_BYTES, stream>>>(q, tm);
+            return cudaGetLastError();
+        }
+    }
     {
         // TMA bulk-store variant (see fft_c2c_bulk_kernel): only when the launcher's contract holds
         if (p.bulk_out && p.in.nseg == 1 && p.out.sN == TB && p.B == TB && (TB * sizeof(cx<T>)) % 16 == 0) {
@@ -46,7 +124,20 @@ static cudaError_t launch_tiled(const FftParams& p, cudaStream_t stream, long lo
             return cudaGetLastError();
         }
     }
-    const unsigned g = unsigned((p.max_ctas > 0 && grid > p.max_ctas) ? p.max_ctas : grid);
+    unsigned g = unsigned((p.max_ctas > 0 && grid > p.max_ctas) ? p.max_ctas : grid);
+    const int cl = env_int("DFFT_CLUSTER", 0);
+    if (cl > 1 && cl <= 8) {
+        // experiment: thread-block clusters of `cl` CTAs = tiles that are adjacent along b are co-scheduled (DRAM page
+        // locality of narrow rows); extra CTAs of the rounded-up grid find no tile and exit
+        g = (g + cl - 1) / cl * cl;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(g); cfg.blockDim = dim3(C::THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, p.inverse ? ki : kf, p);
+    }
     if (p.inverse) ki<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
     else kf<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();

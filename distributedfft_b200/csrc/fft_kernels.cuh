@@ -21,7 +21,10 @@
 // read a per-line table of segment bases from shared memory, and shared-memory indices are a
 // per-thread base plus compile-time constants (SmemLayout in fft_core.cuh).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
+
+#include <type_traits>
 
 #include "fft_core.cuh"
 
@@ -185,7 +188,7 @@ struct CtaFft {
     static constexpr int THREADS = TPL * TB;
     static constexpr int LINES = TILED ? 1 : TB;
     static constexpr size_t TILE_BYTES = size_t(L::ELEMS) * sizeof(cx<T>);
-    static constexpr size_t TABLE_BYTES = size_t(2) * LINES * MAXSEG * sizeof(unsigned long long);
+    static constexpr size_t TABLE_BYTES = size_t(2) * LINES * MAXSEG * sizeof(unsigned long long) + 16;  // + one mbarrier (TMA-fed kernel)
     static constexpr size_t SMEM_BYTES = TILE_BYTES + TABLE_BYTES;
     static_assert(THREADS >= 1 && THREADS <= 1024, "CTA size out of range");
     static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit the 227 KB of shared memory a CTA can use on sm_100a");
@@ -274,7 +277,7 @@ fft_c2c_kernel(const __grid_constant__ FftParams p) {
     using LA = LineAccess<T, C::LINES>;
     using TC = TileCoord<C, TILED, TB>;
     constexpr int E = C::E, TPL = C::TPL;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
     unsigned long long* tab_in = reinterpret_cast<unsigned long long*>(smem_raw + C::TILE_BYTES);
     unsigned long long* tab_out = tab_in + C::LINES * MAXSEG;
@@ -380,7 +383,7 @@ fft_c2c_bulk_kernel(const __grid_constant__ FftParams p) {
     constexpr int E = C::E, TPL = C::TPL, N = C::N;
     // the staging copy of the finished tile is written UNPADDED ([n][TB], N*TB elements <= the padded tile) once the
     // last gather has left the buffer, so narrow (padded) tiles qualify as well
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
     unsigned long long* tab_in = reinterpret_cast<unsigned long long*>(smem_raw + C::TILE_BYTES);
     unsigned long long* tab_out = tab_in + MAXSEG;
@@ -439,6 +442,180 @@ fft_c2c_bulk_kernel(const __grid_constant__ FftParams p) {
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+
+// ---- C2C TILED pass fed by TMA ----------------------------------------------------------------------------
+// Same tile, same stages, but the N x TB input tile is fetched by the TMA engine (cp.async.bulk.tensor, SASS UTMALDG)
+// straight into the tile buffer and announced through an mbarrier, instead of 16 LDG.128 per thread:
+//   * the loads no longer pass through the LSU / L1TEX data pipe — the busiest unit of the register-fed kernel
+//     (ncu: 63-74 % of peak, about half of its wavefronts are the 64-byte-row global accesses);
+//   * no registers are tied to bytes in flight, so the kernel is persistent and the NEXT tile is requested as soon
+//     as the last gather of the current tile has left the buffer: it lands while the last radix stage and the stores
+//     run (and while the second resident CTA computes).
+// Input view: single segment; described by a rank-4 tensor map (b, n, a1, a0) built by the launcher, box TB x 256.
+// Output: either 16-byte stores from registers through any (segmented) view, or — `bulk_out`, blocked hand-over
+// layouts whose rows per destination are adjacent — one cp.async.bulk (UBLKCP) per destination from the buffer.
+struct TmaBar {
+    static __device__ __forceinline__ void init(unsigned long long* bar, unsigned count) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(unsigned(__cvta_generic_to_shared(bar))), "r"(count) : "memory");
+    }
+    static __device__ __forceinline__ void expect(unsigned long long* bar, unsigned bytes) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(unsigned(__cvta_generic_to_shared(bar))), "r"(bytes) : "memory");
+    }
+    // bounded wait: a lost transaction must not hang the GPU (returns false after ~2 s)
+    static __device__ __forceinline__ bool wait(unsigned long long* bar, unsigned parity) {
+        const unsigned a = unsigned(__cvta_generic_to_shared(bar));
+        for (long long spin = 0; spin < (1ll << 26); ++spin) {
+            unsigned ok;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+            if (ok) return true;
+        }
+        return false;
+    }
+};
+
+template <typename T, int LOG2N, int LOG2E, int TB, bool INV>
+__global__ void __launch_bounds__((1 << (LOG2N - LOG2E)) * TB, min_ctas_per_sm<T, LOG2E>((1 << (LOG2N - LOG2E)) * TB))
+fft_c2c_tma_kernel(const __grid_constant__ FftParams p, const __grid_constant__ CUtensorMap tm_in) {
+    using C = CtaFft<T, LOG2N, LOG2E, TB, true>;
+    using Core = typename C::Core;
+    using L = typename C::L;
+    using LA = LineAccess<T, 1>;
+    using TC = TileCoord<C, true, TB>;
+    constexpr int E = C::E, TPL = C::TPL, N = C::N, NST = C::NST;
+    static_assert(NST >= 2, "the TMA-fed kernel is for lines that exchange through shared memory");
+    constexpr unsigned TILE_TX = unsigned(N) * TB * unsigned(sizeof(cx<T>));
+    constexpr int ROWS_PER_OP = N < 256 ? N : 256;  // box height (a TMA box dimension is at most 256)
+    constexpr int D0 = sizeof(T) == 8 ? 2 : 1;      // inner-dimension units per complex element (8-byte units)
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
+    unsigned long long* tab_in = reinterpret_cast<unsigned long long*>(smem_raw + C::TILE_BYTES);
+    unsigned long long* tab_out = tab_in + MAXSEG;
+    unsigned long long* bar = tab_out + MAXSEG;
+    const long long ntiles = TC::num_tiles(p);
+    const bool out_multi = p.out.nseg > 1;
+    const bool bulk = p.bulk_out != 0;
+    const int tid = threadIdx.x;
+
+    auto request = [&](long long tile) {  // one thread: arm the barrier and ask the TMA engine for the tile
+        const TC tc(p, tile);
+        const int b0 = (tc.b - tc.t) * D0;
+        TmaBar::expect(bar, TILE_TX);
+        const unsigned dst = unsigned(__cvta_generic_to_shared(sm));
+        const unsigned mb = unsigned(__cvta_generic_to_shared(bar));
+#pragma unroll
+        for (int r = 0; r < N; r += ROWS_PER_OP)
+            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                         ::"r"(dst + unsigned(r) * TB * unsigned(sizeof(cx<T>))), "l"(&tm_in), "r"(mb), "r"(b0), "r"(r), "r"(tc.a1), "r"(tc.a0)
+                         : "memory");
+    };
+
+    if (tid == 0) {
+        TmaBar::init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0 && (long long)blockIdx.x < ntiles) request(blockIdx.x);
+    unsigned parity = 0;
+
+#pragma unroll 1
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TC tc(p, tile);
+        const int j = tc.j, t = tc.t;
+        const long long next = tile + gridDim.x;
+        if (out_multi && !bulk) LA::fill_table(p.out, tab_out, 0, tid, C::THREADS, tc.a0, tc.a1);
+        if (bulk)
+            for (int s = tid; s < p.out.nseg; s += C::THREADS) {
+                const Seg& g = p.out.seg[s];
+                cx<T>* q = reinterpret_cast<cx<T>*>(g.base) + (tc.a0 * g.sA0 + tc.a1 * g.sA1 - (long long)g.n0 * p.out.sN);
+                tab_out[s] = reinterpret_cast<unsigned long long>(q);
+            }
+        if (!TmaBar::wait(bar, parity)) __trap();
+        parity ^= 1;
+
+        cx<T> v[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const cx<T> x = sm[(j + e * TPL) * TB + t];  // dense [n][TB], as the TMA engine wrote it
+            v[e] = INV ? cswap(x) : x;
+        }
+        __syncthreads();  // everyone has its inputs: the buffer turns into the (padded) exchange space; tables visible
+
+        // the stages of CtaFft::stages, with a hook where the buffer is free again (after the last gather)
+        auto run = [&](auto self, auto st_tag) -> void {
+            constexpr int ST = decltype(st_tag)::value;
+            Core::template stage_compute<ST>(v, j, reinterpret_cast<const cx<T>*>(p.tw));
+            if constexpr (ST + 1 < NST) {
+                if constexpr (ST > 0) __syncthreads();
+                cx<T>* q = sm + L::idx(Core::template scatter_base<ST>(j), t);
+#pragma unroll
+                for (int e = 0; e < E; ++e) q[L::off(Core::template scatter_off<ST>(e))] = v[e];
+                __syncthreads();
+                C::gather(v, sm, j, t);
+                if constexpr (ST + 2 == NST) {
+                    if (!bulk) {
+                        // generic-proxy reads of the buffer are ordered before the async-proxy write of the next tile
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncthreads();
+                        if (tid == 0 && next < ntiles) request(next);
+                    }
+                }
+                self(self, std::integral_constant<int, ST + 1>{});
+            }
+        };
+        run(run, std::integral_constant<int, 0>{});
+
+        if (!bulk) {
+            if (tc.valid) {
+                const LA out(p.out, tab_out, 0, tc.a0, tc.a1, tc.b);
+                if (!out.multi) {
+                    const long long step = (long long)TPL * p.out.sN;
+                    cx<T>* q = out.p0 + (long long)j * p.out.sN;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const cx<T> x = v[Core::final_slot(e)];
+                        st_elem<T>(q, INV ? cswap(x) : x);
+                        q += step;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const cx<T> x = v[Core::final_slot(e)];
+                        st_elem<T>(out.at(j + e * TPL), INV ? cswap(x) : x);
+                    }
+                }
+            }
+            if (out_multi) __syncthreads();  // the segment table is rewritten by the next tile
+        } else {
+            __syncthreads();  // last gather finished everywhere: stage the finished tile, natural order [n][TB]
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const cx<T> x = v[Core::final_slot(e)];
+                sm[(j + e * TPL) * TB + t] = INV ? cswap(x) : x;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                for (int s = 0; s < p.out.nseg; ++s) {
+                    const int n0 = p.out.nseg > 1 ? p.out.seg[s].n0 : 0;
+                    const int n1 = (s + 1 < p.out.nseg) ? p.out.seg[s + 1].n0 : N;
+                    const unsigned bytes = unsigned(n1 - n0) * TB * unsigned(sizeof(cx<T>));
+                    if (!bytes) continue;
+                    const unsigned src = unsigned(__cvta_generic_to_shared(sm + n0 * TB));
+                    const unsigned long long dst = tab_out[s] + (unsigned long long)n0 * TB * sizeof(cx<T>);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the buffer has been read: it may be refilled
+                if (next < ntiles) request(next);
+            }
+            __syncthreads();  // tab_out is rewritten by the next tile
+        }
+    }
+    if (bulk && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores performed before exit
+}
+
 // ---- R2C pass (CONTIG): real line of 2M points -> M+1 complex points ------------------------------------
 // The real line is read as M complex points z[m] = x[2m] + i x[2m+1], transformed with the length-M
 // core and split into even/odd spectra in shared memory:  X[k] = Xe[k] + W_2M^k Xo[k].
@@ -448,7 +625,7 @@ fft_r2c_kernel(const __grid_constant__ FftParams p) {
     using C = CtaFft<T, LOG2M, LOG2E, TB, false>;
     using LA = LineAccess<T, C::LINES>;
     constexpr int E = C::E, TPL = C::TPL, M = C::N, NST = C::NST;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
     unsigned long long* tab_in = reinterpret_cast<unsigned long long*>(smem_raw + C::TILE_BYTES);
     unsigned long long* tab_out = tab_in + C::LINES * MAXSEG;
@@ -504,7 +681,7 @@ fft_c2r_kernel(const __grid_constant__ FftParams p) {
     using C = CtaFft<T, LOG2M, LOG2E, TB, false>;
     using LA = LineAccess<T, C::LINES>;
     constexpr int E = C::E, TPL = C::TPL, M = C::N;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
     unsigned long long* tab_in = reinterpret_cast<unsigned long long*>(smem_raw + C::TILE_BYTES);
     unsigned long long* tab_out = tab_in + C::LINES * MAXSEG;

@@ -68,7 +68,9 @@ static int laplacian(const char* name, Plan& fft, size_t Nx, size_t Ny, size_t N
     }
     std::printf("%s %zux%zux%zu spin=%d  Result (laplacian max / 3sqrt(N)): %.3e\n", name, Nx, Ny, Nz, spin, worst);
     cudaFree(in_d); cudaFree(back_d); cudaFree(out_d);
-    return worst < 1e-12 ? 0 : 1;
+    // rounding grows with the grid (the multiplication by k^2 up to 3 (N/2)^2 amplifies it; the reference records
+    // 7.5e-12 for this check at 1024^3): 1e-10 is BASELINE's bound; an ordering bug shows up as an error of O(1)
+    return worst < 1e-10 ? 0 : 1;
 }
 
 int main() {

@@ -70,10 +70,11 @@ def test_strided_c2c(prec, a, n, b):
     assert O.rel_l2(host(buf), np.fft.fft(x.astype(np.complex128), axis=1)) < TOL[prec]
 
 
-@pytest.mark.parametrize("env", [{"DFFT_WIDE_TILES": "1"}, {"DFFT_WIDE_TILES": "-1"}])
+@pytest.mark.parametrize("env", [{"DFFT_WIDE_TILES": "1"}, {"DFFT_WIDE_TILES": "-1"}, {"DFFT_TMA": "1"}, {"DFFT_TMA": "1", "DFFT_WIDE_TILES": "1"},
+                                 {"DFFT_TMA": "1", "DFFT_TMA_L2PROMO": "2"}, {"DFFT_CLUSTER": "4"}, {"DFFT_CLUSTER": "2", "DFFT_WIDE_TILES": "1"}])
 def test_kernel_variants(env, monkeypatch):
-    """The alternative kernel variants (wide tiles, persistent register-prefetch) are selected by environment
-    variables that the launcher reads at every launch."""
+    """The alternative kernel variants (wide tiles, TMA-fed persistent kernel, cluster launch) are selected by
+    environment variables that the launcher reads at every launch."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     worst = 0.0

@@ -180,7 +180,7 @@ def test_sync_exec_is_ordered_after_default_stream_work():
         back = torch.empty(shape, dtype=torch.float64, device="cuda")
         plan.execC2R(back, out)
         err = np.abs(host(back) - expect).max() / np.abs(expect).max()
-        assert err < 1e-12
+        assert err < 1e-10  # rounding at 256^3 is ~5e-12 (k^2 amplification); a missed ordering edge gives O(1)
     plan.destroy()
 
 

@@ -15,18 +15,23 @@ timeout 1500 $TR --master-port 29513 tools/multi_bench.py \
   "sync:$B --send Sync" \
   "a2a:$B --send Sync --comm All2All" \
   "streams96:$B" \
+  "streams96_notma:$B DFFT_TMA=0" \
+  "streams96_invplain:$B DFFT_BLOCKED_INV=0" \
   "streams96_bulk:$B DFFT_BULK_STORE=1" \
+  "streams48_bulk:$B DFFT_BULK_STORE=1 DFFT_XCHG_CTAS=48" \
+  "streams148:$B DFFT_XCHG_CTAS=148" \
+  "streams48:$B DFFT_XCHG_CTAS=48" \
+  "streams96_c8:$B DFFT_OVL_CHUNKS=8" \
   "narrow4_296:$B DFFT_BLOCKED=4 DFFT_XCHG_WIDE=0 DFFT_XCHG_CTAS=296" \
   "narrow4_148:$B DFFT_BLOCKED=4 DFFT_XCHG_WIDE=0 DFFT_XCHG_CTAS=148" \
   "narrow4_148_bulk:$B DFFT_BLOCKED=4 DFFT_XCHG_WIDE=0 DFFT_XCHG_CTAS=148 DFFT_BULK_STORE=1" \
   "narrow4_74_bulk:$B DFFT_BLOCKED=4 DFFT_XCHG_WIDE=0 DFFT_XCHG_CTAS=74 DFFT_BULK_STORE=1" \
-  "streams48:$B DFFT_XCHG_CTAS=48" \
-  "streams148:$B DFFT_XCHG_CTAS=148" \
   "sync_narrow4:$B --send Sync DFFT_BLOCKED=4 DFFT_XCHG_WIDE=0" \
   "sync_narrow4_bulk:$B --send Sync DFFT_BLOCKED=4 DFFT_XCHG_WIDE=0 DFFT_BULK_STORE=1" \
   "sync_bulk:$B --send Sync DFFT_BULK_STORE=1" \
   "r2c_streams:$B --transform r2c" \
   "r2c_sync:$B --transform r2c --send Sync" \
+  "r2c_streams_bulk:$B --transform r2c DFFT_BULK_STORE=1" \
   > gpurun_out/r02_mb${N}.log 2>&1; echo "multi_bench rc=$?"
 cat gpurun_out/r02_mb${N}.log | grep -v "^\[" | cut -c1-400
 # NVLink counters of the exchanging kernel (single process, kernel replay is safe)
