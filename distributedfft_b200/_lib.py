@@ -84,6 +84,8 @@ SIGNATURES = {
     "dfft_get_step_label": (C.c_char_p, [C.c_void_p, C.c_int]),
     "dfft_get_step_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),
     "dfft_timer_csv_path": (C.c_char_p, [C.c_void_p]),
+    "dfft_plan_tune": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "dfft_plan_tune_report": (C.c_char_p, [C.c_void_p]),
     "dfft_get_timeline": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
     "dfft_get_timeline_label": (C.c_char_p, [C.c_void_p, C.c_int]),
     "dfft_last_error_string": (C.c_char_p, []),

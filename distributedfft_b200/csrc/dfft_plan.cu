@@ -267,8 +267,12 @@ struct dfft_plan_s {
     std::vector<cudaEvent_t> sync_events;
     cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
     int xchg_ctas = 0;                            // SMs given to the exchange pass in overlapped schedules
+    int tuned_seq[2] = {0, 0};                    // dfft_plan_tune: [fwd/inv] 1 = the sequential schedule won
+    int tuned_ctas[2] = {-2, -2};                 // dfft_plan_tune: [fwd/inv] exchange CTAs of the winning overlapped schedule (-2 = not tuned)
+    std::string tune_report;
     int ovl_groups = 4, ovl_chunks = 4;           // overlapped schedules: plane groups of the z pass, z chunks of the y / x passes
     int blocked_ch = 0;                           // > 0: slab forward keeps the y->x intermediate as [b/CH][Nx][CH]
+    int x_swz = 1;                                // tile-order blocking (log2 G) of passes that read the blocked hand-over layout
     int blocked_inv = 1;                          // the inverse x -> y hand-over is blocked as well (DFFT_BLOCKED_INV=0: plain)
     int xchg_tile_pref = 2;                       // tile preference of passes that store into other GPUs (2 = wide rows)
     long long rendezvous_timeout_cycles = 0;      // device clock cycles a rendezvous waits for a peer (0 = forever)
@@ -627,6 +631,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
             else
                 s3.prm.in = single_view(slotp(D2, me), (long long)CH, (long long)(g.nx * oy_i * CH), (long long)(oy_i * CH));
             s3.prm.out = single_view(nullptr, (long long)nz_j, (long long)CH, (long long)(oy_i * nz_j));
+            s3.prm.tile_swz = p->x_swz;
             if (any_rem) {
                 Step s3t = s3;
                 s3t.label = "x pass (tail)";
@@ -901,6 +906,11 @@ namespace dfft {
 // The y pass of chunk c+1 runs while the x pass consumes chunk c, and while later plane groups are still in
 // the z pass.  Inverse: x pass per z chunk scatters (stream 1), y pass per chunk follows (stream 2), the z
 // pass runs last on the caller's stream.
+static int exchange_ctas(const dfft_plan_s* p, int inverse) {
+    const int t = p->tuned_ctas[inverse ? 1 : 0];
+    return t != -2 ? t : p->xchg_ctas;
+}
+
 static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
     const Geometry& g = p->g;
     const int me = p->rank;
@@ -1014,7 +1024,7 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
                     return mkseg(eptr(slotp(D2, r), (x0 + pl0) * nyq * nzc + z0, es), (long long)(nyq * nzc), 0, (long long)nzc, g.oy.start[q]);
                 });
                 }
-                s.prm.max_ctas = p->xchg_ctas;
+                s.prm.max_ctas = exchange_ctas(p, inverse);
                 s.stream = 1;
                 if (c == 0) s.waits.push_back(ev_z[gi]);
                 if (c == 0 && gi == 0) s.waits.push_back(ev_entry);
@@ -1051,6 +1061,7 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
                 s.prm.A0 = int(oy_me); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
                 s.prm.in = single_view(eptr(slotp(D2, me), (z0 / CH) * nx * oy_me * CH, es), (long long)CH, (long long)(nx * oy_me * CH), (long long)(oy_me * CH));
                 s.prm.out = single_view((void*)(size_t)(z0 * es), (long long)nzc, (long long)CH, (long long)(oy_me * nzc));
+                s.prm.tile_swz = p->x_swz;
             } else {
             s.prm.A0 = 1; s.prm.A1 = int(oy_me); s.prm.B = int(zc);
             s.prm.in = single_view(eptr(slotp(D2, me), z0, es), 0, (long long)nzc, (long long)(oy_me * nzc));
@@ -1094,7 +1105,7 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
                     return mkseg(eptr(slotp(D2, r), oy0_me * nzc + z0, es), 0, (long long)nzc, (long long)(ny * nzc), g.sx.start[q]);
                 });
             }
-            s.prm.max_ctas = p->xchg_ctas;
+            s.prm.max_ctas = exchange_ctas(p, inverse);
             s.prm.tile_pref = p->xchg_tile_pref;
             s.stream = 1;
             if (c == 0) s.waits.push_back(ev_entry);
@@ -1312,7 +1323,7 @@ static int build_overlapped_pencil(dfft_plan_s* p, Schedule& sc) {
                     return mkseg(eptr(slotp(D2, r), (x0_i + pl0) * nyq * nz_j + z0, es), (long long)(nyq * nz_j), 0, (long long)nz_j, g.oy.start[q]);
                 });
             }
-            s.prm.max_ctas = p->xchg_ctas;
+            s.prm.max_ctas = exchange_ctas(p, 0);
             s.prm.tile_pref = G2.size() > 1 ? p->xchg_tile_pref : 0;
             s.stream = 1;
             const bool tail_here = CH && any_rem && c + 1 == NS;
@@ -1347,6 +1358,7 @@ static int build_overlapped_pencil(dfft_plan_s* p, Schedule& sc) {
             s.prm.A0 = int(oy_i); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
             s.prm.in = single_view(eptr(slotp(D2, me), (z0 / CH) * nx * oy_i * CH, es), (long long)CH, (long long)(nx * oy_i * CH), (long long)(oy_i * CH));
             s.prm.out = single_view((void*)(size_t)(z0 * es), (long long)nz_j, (long long)CH, (long long)(oy_i * nz_j));
+            s.prm.tile_swz = p->x_swz;
         } else {
             s.prm.A0 = 1; s.prm.A1 = int(oy_i); s.prm.B = int(zc);
             s.prm.in = single_view(eptr(slotp(D2, me), z0, es), 0, (long long)nz_j, (long long)(oy_i * nz_j));
@@ -1630,9 +1642,10 @@ static int get_schedule(dfft_plan_s* p, int inverse, int d, Schedule** out) {
     if (!sc.built) {
         g_view_error = false;
         const bool streams = p->cfg.send_method == DFFT_SEND_STREAMS || (p->g.decomp == DFFT_PENCIL && p->cfg.send_method2 == DFFT_SEND_STREAMS);
-        const bool want_overlap = streams && d == 3 && p->P > 1 && p->g.decomp == DFFT_SLAB_ZY_THEN_X && p->direct2 && p->xchg_ctas >= 0;
+        const bool seq_won = p->tuned_seq[inverse ? 1 : 0] != 0;
+        const bool want_overlap = streams && d == 3 && p->P > 1 && p->g.decomp == DFFT_SLAB_ZY_THEN_X && p->direct2 && p->xchg_ctas >= 0 && !seq_won;
         const bool want_pencil_overlap = streams && d == 3 && !inverse && p->g.decomp == DFFT_PENCIL && p->direct1 && p->direct2 &&
-                                         p->grp[1].size() > 1 && p->grp[2].size() > 1 && p->xchg_ctas >= 0 && pencil_overlap_enabled();
+                                         p->grp[1].size() > 1 && p->grp[2].size() > 1 && p->xchg_ctas >= 0 && pencil_overlap_enabled() && !seq_won;
         int rc;
         if (want_overlap) rc = build_overlapped_slab(p, inverse ? 1 : 0, sc);
         else if (want_pencil_overlap) rc = build_overlapped_pencil(p, sc);
@@ -1904,6 +1917,7 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         const char* ew = getenv("DFFT_XCHG_WIDE");
         p->xchg_tile_pref = (ew && atoi(ew) == 0) ? 1 : 2;
         if (const char* ebi = getenv("DFFT_BLOCKED_INV")) p->blocked_inv = atoi(ebi) != 0;
+        if (const char* esw = getenv("DFFT_X_SWZ")) p->x_swz = std::max(0, std::min(4, atoi(esw)));
         const char* eb = getenv("DFFT_BLOCKED");
         // block width = the widest tile the y and x passes use for these lengths (fft_kernels.cuh: Shape::TBT —
         // 4096 points per tile, rows of at least 64 bytes, at most 32 columns), never below 8 elements
@@ -2148,6 +2162,83 @@ int dfft_get_step_times(dfft_plan_t p, double* ms, int capacity) {
     }
     return n;
 }
+
+// Plan-time measurement of the execution schedule (the role FFTW_MEASURE plays for FFTW plans; the reference leaves
+// the choice between its Sync and Streams variants to the user's benchmarks).  Runs the plan's transform on the
+// caller's buffers with each candidate — the sequential schedule and overlapped schedules with different numbers of
+// CTAs for the exchanging pass — and keeps the fastest one, judged by the slowest rank.  Collective; `out` is
+// overwritten; the input is left intact.  Only plans created with send_method Streams have alternatives.
+int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int reps) {
+    if (!p) return fail(DFFT_ERR_INVALID, "null plan");
+    if (p->comm->dry) return fail(DFFT_ERR_STATE, "geometry-only plan");
+    if (!p->work || !out || !in) return fail(DFFT_ERR_INVALID, "plan needs its work area and both buffers");
+    CK_CUDA(cudaSetDevice(p->comm->device));
+    const int dir = inverse ? 1 : 0;
+    if (reps < 1) reps = 3;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->comm->device);
+    struct Cand { int seq; int ctas; };
+    std::vector<Cand> cands;
+    cands.push_back({1, 0});
+    const bool streams = p->cfg.send_method == DFFT_SEND_STREAMS || (p->g.decomp == DFFT_PENCIL && p->cfg.send_method2 == DFFT_SEND_STREAMS);
+    const bool has_overlap = streams && p->P > 1 && p->xchg_ctas >= 0 &&
+                             ((p->g.decomp == DFFT_SLAB_ZY_THEN_X && p->direct2) ||
+                              (p->g.decomp == DFFT_PENCIL && !inverse && p->direct1 && p->direct2 && p->grp[1].size() > 1 && p->grp[2].size() > 1 &&
+                               pencil_overlap_enabled()));
+    if (has_overlap)
+        for (int c : {sms / 3, (2 * sms) / 3, sms, 2 * sms}) cands.push_back({0, c});
+    p->tune_report.clear();
+    if (cands.size() == 1) {
+        p->tune_report = "sequential schedule (no alternatives for this plan)";
+        return 0;
+    }
+    cudaEvent_t e0, e1;
+    CK_CUDA(cudaEventCreate(&e0));
+    CK_CUDA(cudaEventCreate(&e1));
+    const bool was_timing = p->timing;
+    p->timing = false;
+    int best = 0;
+    double best_ms = 1e30;
+    std::string rep;
+    for (size_t k = 0; k < cands.size(); ++k) {
+        p->tuned_seq[dir] = cands[k].seq;
+        p->tuned_ctas[dir] = cands[k].seq ? -2 : cands[k].ctas;
+        p->sched[dir][2] = Schedule();
+        Schedule* sc = nullptr;
+        int rc = get_schedule(p, inverse, 3, &sc);
+        if (rc) return rc;
+        for (int it = 0; it < reps + 1; ++it) {
+            if (it == 1) CK_CUDA(cudaEventRecord(e0, p->own_stream));
+            rc = run_schedule(p, *sc, out, in, p->own_stream);
+            if (rc) return rc;
+        }
+        CK_CUDA(cudaEventRecord(e1, p->own_stream));
+        rc = dfft_plan_wait(p);
+        if (rc) return rc;
+        float ms = 0;
+        CK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double mine = ms / reps;
+        std::vector<char> all;
+        rc = nccl_allgather_bytes(p, &mine, sizeof(double), all);
+        if (rc) return rc;
+        double worst = 0;
+        for (int r = 0; r < p->P; ++r) worst = std::max(worst, reinterpret_cast<const double*>(all.data())[r]);
+        rep += (k ? ", " : "") + (cands[k].seq ? std::string("sequential") : "overlapped/" + std::to_string(cands[k].ctas) + " CTAs") + " " +
+               std::to_string(worst).substr(0, 6) + " ms";
+        if (worst < best_ms) { best_ms = worst; best = int(k); }
+    }
+    p->tuned_seq[dir] = cands[best].seq;
+    p->tuned_ctas[dir] = cands[best].seq ? -2 : cands[best].ctas;
+    p->sched[dir][2] = Schedule();
+    p->timing = was_timing;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    p->tune_report = std::string(inverse ? "inverse: " : "forward: ") + rep + " -> " +
+                     (cands[best].seq ? std::string("sequential") : "overlapped/" + std::to_string(cands[best].ctas) + " CTAs");
+    return best;
+}
+const char* dfft_plan_tune_report(dfft_plan_t p) { return p ? p->tune_report.c_str() : nullptr; }
+
 // Timeline of the last timed exec: step i ran on plan stream `stream[i]` (0 caller's, 1 exchange, 2 follow-up) from
 // begin_ms[i] to end_ms[i] after the start of the exec.  The way to look at an overlapped (Streams) schedule.
 int dfft_get_timeline(dfft_plan_t p, double* begin_ms, double* end_ms, int* stream, int capacity) {

@@ -70,7 +70,16 @@ static int wide_tiles() {
 }
 
 template <typename T, int LOG2N, int TB>
-static cudaError_t launch_tiled(const FftParams& p, cudaStream_t stream, long long lines) {
+static cudaError_t launch_tiled(const FftParams& p_in, cudaStream_t stream, long long lines) {
+    FftParams p = p_in;
+    {
+        const int e = env_int("DFFT_TILE_SWZ", -1);  // experiment override of the tile-order blocking
+        if (e >= 0) p.tile_swz = e;
+        if (p.tile_swz > 0) {
+            const int G = 1 << p.tile_swz;
+            if (p.tile_swz > 4 || p.A0 % G || p.A1 % G) p.tile_swz = 0;
+        } else p.tile_swz = 0;
+    }
     using S = Shape<T, LOG2N>;
     constexpr int LOG2E = S::LOG2E;
     using C = CtaFft<T, LOG2N, LOG2E, TB, true>;
@@ -82,12 +91,15 @@ static cudaError_t launch_tiled(const FftParams& p, cudaStream_t stream, long lo
     const long long grid = lines * ((p.B + TB - 1) / TB);
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     if constexpr (C::NST >= 2 && LOG2N >= 7) {
-        // TMA-fed persistent kernel (fft_c2c_tma_kernel).  Measured on B200 (tools/axis_bench.py, profiles/r02_axis_*):
-        // 1024-point f64 strided passes +11 % (16 KB pitch), +19 % (far rows), +21 % (blocked hand-over); 512-point f64 and
-        // the f32 tiles lose (their register-fed kernels already run at 0.9+ of the copy bandwidth or use one CTA per
-        // SM), so the default (-1) enables it for f64 lines of 1024 points; DFFT_TMA=1 forces it on, 0 off.
+        // TMA-fed persistent kernel (fft_c2c_tma_kernel).  Measured on B200 (tools/axis_bench.py, profiles/r02/axis_*):
+        // f64 strided passes of 1024 points +7 % (64-byte rows, 16 KB pitch) ... +22 % (128-byte rows) ... +50 % (128-byte
+        // rows, 16 KB pitch: 3876 -> 5838 GB/s), 2048 points +15 ... +40 %, 4096 points +10 ... +23 %; lines of <= 512
+        // points and all f32 tiles lose (their register-fed kernels already run at 0.9+ of the copy bandwidth, or the
+        // tile leaves room for one CTA per SM only), and so do 64-byte rows of the blocked hand-over layout (3009 vs 4044).
+        // Default (-1): f64 lines of >= 1024 points, except 64-byte blocked rows; DFFT_TMA=1 forces it on, 0 off.
         const int mode = env_int("DFFT_TMA", -1);
-        const bool want = mode > 0 || (mode < 0 && sizeof(T) == 8 && LOG2N == 10);
+        const bool narrow_blocked = p.B == TB && TB * sizeof(cx<T>) < 128;
+        const bool want = mode > 0 || (mode < 0 && sizeof(T) == 8 && LOG2N >= 10 && !narrow_blocked);
         const bool bulk_ok = p.bulk_out && p.out.sN == TB && p.B == TB;
         alignas(64) CUtensorMap tm;
         if (want && p.in.nseg == 1 && (!p.bulk_out || bulk_ok) && make_view_map<T>(p.in, p.A0, p.A1, C::N, p.B, TB, &tm)) {
@@ -172,8 +184,12 @@ cudaError_t launch_pass(PassKind kind, const FftParams& p, cudaStream_t stream) 
                 const int w = wide_tiles();
                 const bool far_rows = (unsigned long long)p.in.sN * sizeof(cx<T>) >= (1ull << 20) ||
                                       (unsigned long long)p.out.sN * sizeof(cx<T>) >= (1ull << 20);
-                const bool wide = w > 0 || p.tile_pref == 2 || (w == 0 && p.tile_pref == 0 && LOG2N >= 10 && far_rows);
-                if (wide && w >= 0 && p.tile_pref != 1) return launch_tiled<T, LOG2N, S::TBT_WIDE>(p, stream, lines);
+                // with the TMA-fed kernel (f64, >= 1024 points) the wide tile wins for near rows as well (5838 vs 5089 GB/s)
+                const bool tma_auto = env_int("DFFT_TMA", -1) != 0 && sizeof(T) == 8 && LOG2N >= 10 && p.in.nseg == 1;
+                const bool wide = w > 0 || p.tile_pref == 2 || (w == 0 && p.tile_pref == 0 && LOG2N >= 10 && (far_rows || tma_auto));
+                // never a wide tile for a view that is only one narrow tile wide (blocked hand-over with CH = TBT): half of
+                // its columns would be empty
+                if (wide && w >= 0 && p.tile_pref != 1 && p.B > S::TBT) return launch_tiled<T, LOG2N, S::TBT_WIDE>(p, stream, lines);
             }
             return launch_tiled<T, LOG2N, S::TBT>(p, stream, lines);
         }

@@ -60,7 +60,9 @@ struct FftParams {
                       // overlapped schedule: the exchange pass keeps a few SMs, the local passes the rest)
     int tile_pref;    // TILED: 0 automatic, 1 narrow tiles, 2 wide tiles
     int bulk_out;     // TILED, experimental: store each destination's rows with one cp.async.bulk (TMA) from shared memory
-    int pad2_;
+    int tile_swz;     // TILED: log2 G of the tile-order blocking: G x G tiles of (a0, a1) are numbered consecutively, so
+                      // that CTAs running at the same time touch neighbouring rows on BOTH sides of a transposing pass
+                      // (0 = plain order: b tiles fastest, then a1, then a0)
 };
 
 enum PassKind { PASS_C2C_CONTIG = 0, PASS_C2C_TILED = 1, PASS_R2C = 2, PASS_C2R = 3 };
@@ -235,6 +237,24 @@ struct CtaFft {
     }
 };
 
+// linear tile number -> (b tile, a1, a0) of a TILED pass
+template <int TB>
+__device__ __forceinline__ void tiled_decode(const FftParams& p, long long tile, int& bt, int& a1, int& a0) {
+    const int nbt = (p.B + TB - 1) / TB;
+    bt = int(tile % nbt);
+    const int a = int(tile / nbt);
+    if (p.tile_swz > 0) {
+        const int lg = p.tile_swz, G = 1 << lg;
+        const int lo = a & (G * G - 1), hi = a >> (2 * lg);
+        const int w1 = p.A1 >> lg;  // A0, A1 are multiples of G (checked by the launcher)
+        a1 = ((hi % w1) << lg) + (lo & (G - 1));
+        a0 = ((hi / w1) << lg) + (lo >> lg);
+    } else {
+        a1 = a % p.A1;
+        a0 = a / p.A1;
+    }
+}
+
 // common prologue: thread -> (j, t), tile -> (a0, a1, b), segment tables
 template <typename C, bool TILED, int TB>
 struct TileCoord {
@@ -245,13 +265,10 @@ struct TileCoord {
         if constexpr (TILED) { t = tid % TB; j = tid / TB; }
         else { j = tid % C::TPL; t = tid / C::TPL; }
         if constexpr (TILED) {
-            const int nbt = (p.B + TB - 1) / TB;
-            const int bt = int(tile % nbt);
-            const int a = int(tile / nbt);
+            int bt;
+            tiled_decode<TB>(p, tile, bt, a1, a0);
             b = bt * TB + t;
             valid = b < p.B;
-            a1 = a % p.A1;
-            a0 = a / p.A1;
         } else {
             const long long line = tile * TB + t;
             valid = line < (long long)p.A0 * p.A1;
@@ -615,6 +632,7 @@ fft_c2c_tma_kernel(const __grid_constant__ FftParams p, const __grid_constant__ 
     }
     if (bulk && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores performed before exit
 }
+
 
 // ---- R2C pass (CONTIG): real line of 2M points -> M+1 complex points ------------------------------------
 // The real line is read as M complex points z[m] = x[2m] + i x[2m+1], transformed with the length-M

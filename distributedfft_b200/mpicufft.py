@@ -173,6 +173,13 @@ class MPIcuFFT:
     def wait(self):
         return check(lib().dfft_plan_wait(self._h))
 
+    def tune(self, out, in_, direction: int = FORWARD, reps: int = 3) -> str:
+        """Plan-time measurement: try the sequential and the overlapped schedules on these buffers and keep the fastest
+        (collective).  Returns the report string."""
+        self._need()
+        check(lib().dfft_plan_tune(self._h, _ptr(out), _ptr(in_), 1 if direction > 0 else 0, reps))
+        return (lib().dfft_plan_tune_report(self._h) or b"").decode()
+
     # -- getters ---------------------------------------------------------------------------------
     def _triple(self, fn, *a):
         v = (C.c_size_t * 3)()

@@ -150,6 +150,15 @@ int dfft_partition(size_t n, size_t parts, size_t* sizes, size_t* starts);
 int dfft_layout(int decomp, int transform, size_t nx, size_t ny, size_t nz, size_t p1, size_t p2,
                 int rank, int which, size_t size[3], size_t start[3]);
 
+/* ---- plan-time measurement ---------------------------------------------------------------------------------
+ * The reference offers Sync and Streams variants of every transposition and leaves the choice to the user's own
+ * benchmark sweeps (jobs/ ** /benchmarks_base.json).  dfft_plan_tune makes it once, at plan time, like FFTW_MEASURE:
+ * it runs the transform on the caller's buffers with the sequential schedule and with overlapped schedules that give the
+ * exchanging pass different numbers of CTAs, and keeps the fastest (slowest rank decides).  Collective; `out` is
+ * overwritten, `in` is not.  Only plans with send_method Streams have alternatives.  Returns the candidate index. */
+int dfft_plan_tune(dfft_plan_t plan, void* out, const void* in, int inverse, int reps);
+const char* dfft_plan_tune_report(dfft_plan_t plan);
+
 /* ---- phase timer (include/timer.hpp, src/timer.cpp; section names mpicufft_slab.hpp:209-223,
  *      mpicufft_pencil.hpp:263-287) -------------------------------------------------------------------
  * Cumulative milliseconds since the start of the last exec, measured with CUDA events. */

@@ -292,6 +292,21 @@ def test_timer_csv_schema(tmp_path):
     plan.destroy()
 
 
+def test_step_timeline():
+    """dfft_get_timeline: (label, stream, begin, end) of every step of the last timed exec"""
+    shape = (64, 64, 64)
+    plan = make_plan(dfft.MPIcuFFT_Slab, dfft.F64, dfft.C2C, shape)
+    x = dev(O.complex_input(shape))
+    out = torch.empty(shape, dtype=torch.complex128, device="cuda")
+    plan.enableTimer(True)
+    plan.execC2C(out, x, dfft.FORWARD)
+    tl = plan.timeline()
+    assert [l for l, _, _, _ in tl] == ["z pass", "y pass", "x pass"]
+    assert all(st == 0 and 0 <= b <= e for _, st, b, e in tl)
+    assert tl[0][3] <= tl[1][2] + 1e-3 and tl[1][3] <= tl[2][2] + 1e-3  # sequential schedule: one after the other
+    plan.destroy()
+
+
 @pytest.mark.parametrize("argv", [
     ["slab", "-nx", "64", "-ny", "64", "-nz", "64", "-t", "1", "-d"],
     ["slab", "-nx", "64", "-ny", "32", "-nz", "128", "-t", "3", "-s", "Z_Then_YX", "-i", "2"],
