@@ -231,6 +231,7 @@ struct Schedule {
     std::vector<Step> steps;
     bool built = false;
     bool overlapped = false;  // uses the plan's auxiliary streams
+    bool prio_swap = false;   // ... the pair in which the follow-up passes outrank the exchanging pass
     int nevents = 0;
 };
 
@@ -263,7 +264,9 @@ struct dfft_plan_s {
     int* err_d = nullptr;
     unsigned long long epoch = 0;
     unsigned long long ticket[4] = {0, 0, 0, 0};  // per-phase rendezvous counters (same sequence on every rank)
-    cudaStream_t aux[2] = {nullptr, nullptr};     // exchange stream (high priority), follow-up stream
+    cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};  // exchange (high priority), follow-up (low); swapped pair: exchange (low), follow-up (high)
+    int ovl_prio_swap = 0;                        // overlapped schedules use the swapped pair (DFFT_OVL_PRIO_SWAP)
+    int tuned_swap[2] = {-1, -1};                 // dfft_plan_tune: [fwd/inv] priority pair of the winning schedule (-1 = not tuned)
     std::vector<cudaEvent_t> sync_events;
     cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
     int xchg_ctas = 0;                            // SMs given to the exchange pass in overlapped schedules
@@ -1536,7 +1539,8 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
     int launches = 0;
     int ev = 0;
     const bool timing = p->timing;
-    cudaStream_t streams[3] = {st, p->aux[0], p->aux[1]};
+    cudaStream_t const ax0 = sc.prio_swap ? p->aux[2] : p->aux[0], ax1 = sc.prio_swap ? p->aux[3] : p->aux[1];
+    cudaStream_t streams[3] = {st, ax0, ax1};
     auto mark = [&](const char* name, int is_fft, const char* label = "") -> cudaError_t {
         if (!timing || (sc.overlapped && is_fft != -1)) return cudaSuccess;  // overlapped: only start / end are meaningful
         if (ev >= int(p->events.size())) {
@@ -1560,8 +1564,8 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
             p->sync_events.push_back(e);
         }
         CK_CUDA(cudaEventRecord(p->fork_ev, st));
-        CK_CUDA(cudaStreamWaitEvent(p->aux[0], p->fork_ev, 0));
-        CK_CUDA(cudaStreamWaitEvent(p->aux[1], p->fork_ev, 0));
+        CK_CUDA(cudaStreamWaitEvent(ax0, p->fork_ev, 0));
+        CK_CUDA(cudaStreamWaitEvent(ax1, p->fork_ev, 0));
     }
     CK_CUDA(mark("start", -1));
     int tl = 0;
@@ -1624,7 +1628,7 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
     if (timing) p->tl_used = tl;
     if (sc.overlapped) {
         for (int a = 0; a < 2; ++a) {
-            CK_CUDA(cudaEventRecord(p->join_ev[a], p->aux[a]));
+            CK_CUDA(cudaEventRecord(p->join_ev[a], a == 0 ? ax0 : ax1));
             CK_CUDA(cudaStreamWaitEvent(st, p->join_ev[a], 0));
         }
     }
@@ -1652,6 +1656,8 @@ static int get_schedule(dfft_plan_s* p, int inverse, int d, Schedule** out) {
         else rc = build_schedule(p, inverse ? 1 : 0, d, sc);
         if (rc) return rc;
         if (g_view_error) return fail(DFFT_ERR_STATE, "internal: segments of one view disagree on the axis stride");
+        const int ts = p->tuned_swap[inverse ? 1 : 0];
+        sc.prio_swap = sc.overlapped && (ts >= 0 ? ts != 0 : p->ovl_prio_swap != 0);
     }
     *out = &sc;
     return DFFT_SUCCESS;
@@ -1907,6 +1913,7 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         // NVLink store efficiency grows with the contiguous run per row: 64-byte rows reach 434 GB/s per direction,
         // 128-byte rows 700 GB/s, 2 KB runs 704 GB/s (profiles/r01_8gpu, r01_bench_n2_*): exchanging passes prefer the
         // wide tile even though it is slower as a purely local pass.  DFFT_XCHG_WIDE=0 keeps the narrow tile.
+        if (const char* ps = getenv("DFFT_OVL_PRIO_SWAP")) p->ovl_prio_swap = atoi(ps) != 0;
         if (const char* eg = getenv("DFFT_OVL_GROUPS")) p->ovl_groups = std::max(1, std::min(16, atoi(eg)));
         if (const char* ec = getenv("DFFT_OVL_CHUNKS")) p->ovl_chunks = std::max(1, std::min(16, atoi(ec)));
         const char* et = getenv("DFFT_RENDEZVOUS_TIMEOUT_S");
@@ -1953,6 +1960,8 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
         if (cudaStreamCreateWithPriority(&p->aux[0], cudaStreamNonBlocking, hi) != cudaSuccess ||
             cudaStreamCreateWithPriority(&p->aux[1], cudaStreamNonBlocking, lo) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&p->aux[2], cudaStreamNonBlocking, lo) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&p->aux[3], cudaStreamNonBlocking, hi) != cudaSuccess ||
             cudaEventCreateWithFlags(&p->fork_ev, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&p->join_ev[0], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&p->join_ev[1], cudaEventDisableTiming) != cudaSuccess) {
@@ -2008,10 +2017,10 @@ int dfft_plan_destroy(dfft_plan_t p) {
     for (cudaEvent_t e : p->tl_events) cudaEventDestroy(e);
     for (cudaEvent_t e : p->sync_events) cudaEventDestroy(e);
     if (p->fork_ev) cudaEventDestroy(p->fork_ev);
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < 2; ++a)
         if (p->join_ev[a]) cudaEventDestroy(p->join_ev[a]);
+    for (int a = 0; a < 4; ++a)
         if (p->aux[a]) cudaStreamDestroy(p->aux[a]);
-    }
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     if (p->entry_ev) cudaEventDestroy(p->entry_ev);
     delete p;
@@ -2168,6 +2177,10 @@ int dfft_get_step_times(dfft_plan_t p, double* ms, int capacity) {
 // caller's buffers with each candidate — the sequential schedule and overlapped schedules with different numbers of
 // CTAs for the exchanging pass — and keeps the fastest one, judged by the slowest rank.  Collective; `out` is
 // overwritten; the input is left intact.  Only plans created with send_method Streams have alternatives.
+static std::string cand_name(int seq, int ctas, int swap) {
+    if (seq) return "sequential";
+    return "overlapped/" + (ctas > 0 ? std::to_string(ctas) + " CTAs" : std::string("full grid")) + (swap ? "/local passes first" : "");
+}
 int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int reps) {
     if (!p) return fail(DFFT_ERR_INVALID, "null plan");
     if (p->comm->dry) return fail(DFFT_ERR_STATE, "geometry-only plan");
@@ -2177,16 +2190,20 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
     if (reps < 1) reps = 3;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->comm->device);
-    struct Cand { int seq; int ctas; };
+    struct Cand { int seq; int ctas; int swap; };
     std::vector<Cand> cands;
-    cands.push_back({1, 0});
+    cands.push_back({1, 0, 0});
     const bool streams = p->cfg.send_method == DFFT_SEND_STREAMS || (p->g.decomp == DFFT_PENCIL && p->cfg.send_method2 == DFFT_SEND_STREAMS);
     const bool has_overlap = streams && p->P > 1 && p->xchg_ctas >= 0 &&
                              ((p->g.decomp == DFFT_SLAB_ZY_THEN_X && p->direct2) ||
                               (p->g.decomp == DFFT_PENCIL && !inverse && p->direct1 && p->direct2 && p->grp[1].size() > 1 && p->grp[2].size() > 1 &&
                                pencil_overlap_enabled()));
-    if (has_overlap)
-        for (int c : {sms / 3, (2 * sms) / 3, sms, 2 * sms}) cands.push_back({0, c});
+    if (has_overlap) {
+        // exchange pass as a capped persistent grid that outranks the local passes ...
+        for (int c : {sms / 3, (2 * sms) / 3, sms, 2 * sms}) cands.push_back({0, c, 0});
+        // ... or at full size but outranked by them (the local passes take every CTA slot that frees up)
+        for (int c : {0, sms}) cands.push_back({0, c, 1});
+    }
     p->tune_report.clear();
     if (cands.size() == 1) {
         p->tune_report = "sequential schedule (no alternatives for this plan)";
@@ -2203,6 +2220,7 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
     for (size_t k = 0; k < cands.size(); ++k) {
         p->tuned_seq[dir] = cands[k].seq;
         p->tuned_ctas[dir] = cands[k].seq ? -2 : cands[k].ctas;
+        p->tuned_swap[dir] = cands[k].swap;
         p->sched[dir][2] = Schedule();
         Schedule* sc = nullptr;
         int rc = get_schedule(p, inverse, 3, &sc);
@@ -2223,18 +2241,17 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
         if (rc) return rc;
         double worst = 0;
         for (int r = 0; r < p->P; ++r) worst = std::max(worst, reinterpret_cast<const double*>(all.data())[r]);
-        rep += (k ? ", " : "") + (cands[k].seq ? std::string("sequential") : "overlapped/" + std::to_string(cands[k].ctas) + " CTAs") + " " +
-               std::to_string(worst).substr(0, 6) + " ms";
+        rep += (k ? ", " : "") + cand_name(cands[k].seq, cands[k].ctas, cands[k].swap) + " " + std::to_string(worst).substr(0, 6) + " ms";
         if (worst < best_ms) { best_ms = worst; best = int(k); }
     }
     p->tuned_seq[dir] = cands[best].seq;
     p->tuned_ctas[dir] = cands[best].seq ? -2 : cands[best].ctas;
+    p->tuned_swap[dir] = cands[best].swap;
     p->sched[dir][2] = Schedule();
     p->timing = was_timing;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    p->tune_report = std::string(inverse ? "inverse: " : "forward: ") + rep + " -> " +
-                     (cands[best].seq ? std::string("sequential") : "overlapped/" + std::to_string(cands[best].ctas) + " CTAs");
+    p->tune_report = std::string(inverse ? "inverse: " : "forward: ") + rep + " -> " + cand_name(cands[best].seq, cands[best].ctas, cands[best].swap);
     return best;
 }
 const char* dfft_plan_tune_report(dfft_plan_t p) { return p ? p->tune_report.c_str() : nullptr; }
