@@ -134,6 +134,21 @@ def run_case(P, decomp, transform, shape, p1, p2, comm_method, send_method, inve
             if st["type"] == 1:
                 last_rdv[r] = k
                 continue
+            if st["type"] == 3:  # pusher: strided byte copies from a local staging slot into the peers' slots
+                for dsc in st["descs"]:
+                    own_src = owner_of(dsc["src"])
+                    assert own_src is not None and own_src[0] == r, "the pusher reads local memory only"
+                    own_dst = owner_of(dsc["dst"])
+                    assert own_dst is not None and own_dst[0] != r
+                    assert last_rdv[r] >= 0, f"rank {r} pushes into rank {own_dst[0]}'s slot before its entry rendezvous"
+                    last_remote_write[own_dst] = k
+                    assert dsc["row_bytes"] % 16 == 0 and dsc["src_pitch"] % 16 == 0 and dsc["dst_pitch"] % 16 == 0
+                    n16 = dsc["row_bytes"] // 16
+                    for row in range(dsc["rows"]):
+                        src, so = mem.resolve(dsc["src"] + row * dsc["src_pitch"])
+                        dst, do = mem.resolve(dsc["dst"] + row * dsc["dst_pitch"])
+                        pending.append((dst, do, src[so:so + n16].copy()))
+                continue
             if st["type"] == 2:  # all-to-all-v between staging slots
                 sb = scheds[r]["slots"][st["send_slot"]][r]
                 for peer in st["peers"]:
@@ -265,6 +280,21 @@ def test_layout_knobs(env, inverse, monkeypatch):
     assert run_case(4, SL, dfft.R2C, (8, 16, 128), 4, 1, P2P, STREAMS, inverse, 3) < 1e-12
     assert run_case(2, SL, dfft.R2C, (8, 8, 256), 2, 1, A2A, SYNC, inverse, 3) < 1e-12
     assert run_case(4, PE, dfft.R2C, (8, 16, 512), 2, 2, P2P, SYNC, inverse, 3) < 1e-12
+
+
+@pytest.mark.parametrize("P,transform,shape", [(8, dfft.C2C, (32, 16, 256)), (2, dfft.C2C, (8, 8, 128)), (8, dfft.R2C, (16, 8, 512)), (3, dfft.R2C, (16, 16, 256)),
+                                               (4, dfft.C2C, (128, 128, 128)), (4, dfft.R2C, (64, 32, 1024))])
+def test_staged_slab_schedule(P, transform, shape, monkeypatch):
+    """overlapped slab schedule with a local y pass and the pusher (DFFT_STAGED=1, SendMethod Streams), forward; the
+    inverse of the same plan keeps the fused overlapped schedule"""
+    monkeypatch.setenv("DFFT_STAGED", "1")
+    assert run_case(P, SL, transform, shape, P, 1, P2P, STREAMS, 0, 3) < 1e-12
+    sched = describe(0, P, SL, transform, shape, P, 1, P2P, STREAMS, 0, 3)
+    assert sched["overlapped"] and any(s["type"] == 3 for s in sched["steps"]) and sched["nslots"] == 3
+    assert {s["stream"] for s in sched["steps"]} == {0, 1, 2, 3}
+    assert run_case(P, SL, transform, shape, P, 1, P2P, STREAMS, 1, 3) < 1e-12
+    monkeypatch.delenv("DFFT_STAGED")
+    assert not any(s["type"] == 3 for s in describe(0, P, SL, transform, shape, P, 1, P2P, STREAMS, 0, 3)["steps"])
 
 
 @pytest.mark.parametrize("shape,P", [((128, 128, 128), 4), ((64, 256, 256), 2), ((256, 64, 128), 8), ((16, 16, 128), 1)])

@@ -12,11 +12,17 @@ timeout 1500 $TR --master-port 29513 tools/multi_bench.py \
   "ovl148_swap:$B --no-tune DFFT_XCHG_CTAS=148 DFFT_OVL_PRIO_SWAP=1" \
   "ovl_full_swap_c8:$B --no-tune DFFT_XCHG_CTAS=0 DFFT_OVL_PRIO_SWAP=1 DFFT_OVL_CHUNKS=8" \
   "ovl_full_swap_g1:$B --no-tune DFFT_XCHG_CTAS=0 DFFT_OVL_PRIO_SWAP=1 DFFT_OVL_GROUPS=1" \
+  "staged32:$B --no-tune DFFT_STAGED=1" \
+  "staged64:$B --no-tune DFFT_STAGED=1 DFFT_PUSH_CTAS=64" \
+  "staged16:$B --no-tune DFFT_STAGED=1 DFFT_PUSH_CTAS=16" \
+  "staged32_c8:$B --no-tune DFFT_STAGED=1 DFFT_OVL_CHUNKS=8" \
+  "staged32_g2:$B --no-tune DFFT_STAGED=1 DFFT_OVL_GROUPS=2" \
+  "r2c_staged32:$B --no-tune --transform r2c DFFT_STAGED=1" \
   "r2c_tuned:$B --transform r2c" \
   "r2c_ovl_full_swap:$B --no-tune --transform r2c DFFT_XCHG_CTAS=0 DFFT_OVL_PRIO_SWAP=1" \
   > gpurun_out/r02_mb${N}c.log 2>&1; echo "multi_bench rc=$?"
 grep -v "^\[\|^\*\|^Setting\|NCCL version\|^$" gpurun_out/r02_mb${N}c.log | cut -c1-330
-for f in tuned ovl98 ovl148 ovl_full_swap ovl148_swap ovl_full_swap_g1; do python - "$f" "$N" <<'PY'
+for f in tuned ovl98 ovl148 ovl_full_swap staged32 staged32_c8 r2c_staged32; do python - "$f" "$N" <<'PY'
 import json,sys
 name=sys.argv[1]; n=sys.argv[2]
 try:
