@@ -321,6 +321,7 @@ struct dfft_plan_s {
     cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};  // exchange (high priority), follow-up (low); swapped pair: exchange (low), follow-up (high)
     int staged = 0;                               // overlapped slab forward uses the staged ("pusher") schedule (DFFT_STAGED)
     int tuned_staged[2] = {-1, -1};
+    int tuned_push[2] = {0, 0};                   // dfft_plan_tune: CTAs of the pusher, per direction (0 = push_ctas)
     int push_ctas = 32;                           // CTAs of the push kernel (DFFT_PUSH_CTAS)
     int ovl_prio_swap = 0;                        // overlapped schedules use the swapped pair (DFFT_OVL_PRIO_SWAP)
     int tuned_swap[2] = {-1, -1};                 // dfft_plan_tune: [fwd/inv] priority pair of the winning schedule (-1 = not tuned)
@@ -389,6 +390,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc);
 static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc);
 static int build_overlapped_pencil(dfft_plan_s* p, Schedule& sc);
 static int build_staged_slab(dfft_plan_s* p, Schedule& sc);
+static int build_staged_slab_inverse(dfft_plan_s* p, Schedule& sc);
 static bool pencil_overlap_enabled();
 
 }  // namespace dfft
@@ -1592,7 +1594,7 @@ static int build_staged_slab(dfft_plan_s* p, Schedule& sc) {
             ps.type = STEP_PUSH;
             ps.label = "push";
             ps.stream = 3;
-            ps.push_ctas = p->push_ctas;
+            ps.push_ctas = p->tuned_push[0] > 0 ? p->tuned_push[0] : p->push_ctas;
             ps.waits.push_back(ev_y);
             for (size_t q = 0; q < G2.size(); ++q) {
                 const int r = G2[q];
@@ -1649,6 +1651,211 @@ static int build_staged_slab(dfft_plan_s* p, Schedule& sc) {
             sc.steps.push_back(t);
         }
     }
+    sc.nevents = nev;
+    sc.built = true;
+    return DFFT_SUCCESS;
+}
+
+}  // namespace dfft
+
+
+namespace dfft {
+
+// Staged overlapped slab schedule, inverse: x pass per z chunk as a local pass into the staging slot (receivers' blocked
+// layout [nzc/CH][ny][nx_q][CH], own block straight into the own slot), pusher, then per chunk rendezvous + y pass, z pass last.
+static int build_staged_slab_inverse(dfft_plan_s* p, Schedule& sc) {
+    const Geometry& g = p->g;
+    const int me = p->rank;
+    const size_t es = p->esize;
+    const bool c2c = g.transform == DFFT_C2C;
+    Tables& T = p->tabs;
+    sc.steps.clear();
+    sc.overlapped = true;
+    const size_t nzc = g.nzc, ny = g.ny, nx = g.nx;
+    const size_t nx_p = g.sx.size[me];
+    const size_t oy_me = g.oy.size[me], oy0_me = g.oy.start[me];
+    const std::vector<int>& G2 = p->grp[2];
+    const int D1 = 0, D2 = 1, SS = 2;
+    if (p->nslots < 3) return fail(DFFT_ERR_STATE, "internal: staged schedule needs a staging slot");
+    auto slotp = [&](int s_, int r) -> void* { return p->slot_ptr[s_][r]; };
+    int nev = 0;
+    const size_t CH = size_t(p->blocked_ch);
+    if (!CH) return fail(DFFT_ERR_STATE, "internal: staged schedule needs the blocked hand-over layout");
+    const size_t rem = nzc % CH, nzm = nzc - rem;
+    (void)nx;
+
+    auto new_pass = [&](PassKind kind, size_t n, const char* label, Step& s) -> int {
+        s = Step();
+        s.type = STEP_PASS;
+        s.kind = kind;
+        s.label = label;
+        s.log2n = ilog2_exact(n);
+        if (s.log2n < 1 || s.log2n > MAX_LOG2N) return fail(DFFT_ERR_UNSUPPORTED, "unsupported axis length");
+        s.prm.A0 = 1; s.prm.A1 = 1; s.prm.B = 1;
+        s.prm.inverse = 1;
+        void* tw = nullptr;
+        if (T.get_tw(s.log2n, &tw) != cudaSuccess) return fail(DFFT_ERR_CUDA, "twiddle table allocation failed");
+        s.prm.tw = tw;
+        if (kind == PASS_C2R) {
+            void* tw2 = nullptr;
+            if (T.get_tw2(s.log2n, &tw2) != cudaSuccess) return fail(DFFT_ERR_CUDA, "twiddle table allocation failed");
+            s.prm.tw2 = tw2;
+        }
+        return DFFT_SUCCESS;
+    };
+    auto rendezvous = [&](int group, int phase_id, int stream) {
+        Step s;
+        s.type = STEP_RENDEZVOUS;
+        s.label = group == 0 ? "entry rendezvous" : "rendezvous 2";
+        s.group = group;
+        s.phase_id = phase_id;
+        s.stream = stream;
+        return s;
+    };
+
+    Split chunks;
+    const size_t NSw = nzc >= 32 * size_t(p->ovl_chunks) ? size_t(p->ovl_chunks) : (nzc >= 32 ? 2 : 1);
+    {
+        Split u;
+        u.make(nzm / CH, std::min<size_t>(NSw, nzm / CH));
+        for (size_t c = 0; c < u.size.size(); ++c) { chunks.size.push_back(u.size[c] * CH); chunks.start.push_back(u.start[c] * CH); }
+    }
+    const size_t NSc = chunks.size.size();
+    const unsigned char* tab_x = nullptr;
+    if (T.seg_table(g.sx, &tab_x) != cudaSuccess) return fail(DFFT_ERR_CUDA, "segment table");
+    // staging slot: per destination q a region [nzm/CH][oy_me][nx_q][CH] followed by its tail [nx_q][oy_me][rem]
+    std::vector<size_t> soff(G2.size(), 0);
+    {
+        size_t o = 0;
+        for (size_t q = 0; q < G2.size(); ++q) { soff[q] = o; o += oy_me * g.sx.size[q] * nzc; }
+    }
+
+    sc.steps.push_back(rendezvous(0, 0, 0));
+    const int ev_entry = nev++;
+    sc.steps.back().record = ev_entry;
+    int rc;
+    std::vector<int> ev_p(NSc), ev_y(NSc);
+    for (size_t c = 0; c < NSc; ++c) {
+        const size_t z0 = chunks.start[c], zc = chunks.size[c];
+        const bool tail_here = rem && c + 1 == NSc;
+        Step s;
+        rc = new_pass(PASS_C2C_TILED, nx, "x pass", s);
+        if (rc) return rc;
+        s.in_user = 1;
+        s.prm.A0 = int(oy_me); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
+        s.prm.in = single_view((void*)(size_t)(z0 * es), (long long)nzc, (long long)CH, (long long)(oy_me * nzc));
+        seg_view(s.prm.out, tab_x, G2, [&](int q, int r) {
+            const size_t nxq = g.sx.size[q];
+            if (r == me)
+                return mkseg(eptr(slotp(D2, me), ((z0 / CH) * ny + oy0_me) * nxq * CH, es), (long long)(nxq * CH), (long long)(ny * nxq * CH), (long long)CH, g.sx.start[q]);
+            return mkseg(eptr(slotp(SS, me), soff[q] + (z0 / CH) * oy_me * nxq * CH, es), (long long)(nxq * CH), (long long)(oy_me * nxq * CH), (long long)CH, g.sx.start[q]);
+        });
+        s.stream = 1;
+        if (c == 0) s.waits.push_back(ev_entry);
+        const int ev_x = nev++;
+        if (!tail_here) s.record = ev_x;
+        sc.steps.push_back(s);
+        if (tail_here) {
+            Step t = s;
+            t.label = "x pass (tail)";
+            t.waits.clear();
+            t.prm.A0 = int(oy_me); t.prm.A1 = 1; t.prm.B = int(rem);
+            t.prm.in = single_view((void*)(size_t)(nzm * es), (long long)nzc, 0, (long long)(oy_me * nzc));
+            // every segment of a view shares one stride along x: the own tail block is staged as well and copied by the pusher
+            seg_view(t.prm.out, tab_x, G2, [&](int q, int) {
+                const size_t nxq = g.sx.size[q];
+                return mkseg(eptr(slotp(SS, me), soff[q] + oy_me * nxq * nzm, es), (long long)rem, 0, (long long)(oy_me * rem), g.sx.start[q]);
+            });
+            t.record = ev_x;
+            sc.steps.push_back(t);
+        }
+        Step ps;
+        ps.type = STEP_PUSH;
+        ps.label = "push";
+        ps.stream = 3;
+        ps.push_ctas = p->tuned_push[1] > 0 ? p->tuned_push[1] : p->push_ctas;
+        ps.waits.push_back(ev_x);
+        for (size_t q = 0; q < G2.size(); ++q) {
+            const int r = G2[q];
+            const size_t nxq = g.sx.size[q];
+            if (r == me) {
+                if (tail_here) {  // own tail block: staging -> own slot (local copy)
+                    PushDesc e{};
+                    e.src = (const char*)eptr(slotp(SS, me), soff[q] + oy_me * nxq * nzm, es);
+                    e.dst = (char*)eptr(slotp(D2, me), ny * nxq * nzm + oy0_me * rem, es);
+                    e.row_bytes = oy_me * rem * es;
+                    e.src_pitch = e.row_bytes;
+                    e.dst_pitch = ny * rem * es;
+                    e.rows = int(nxq);
+                    ps.push.push_back(e);
+                }
+                continue;
+            }
+            PushDesc d{};
+            d.src = (const char*)eptr(slotp(SS, me), soff[q] + (z0 / CH) * oy_me * nxq * CH, es);
+            d.dst = (char*)eptr(slotp(D2, r), ((z0 / CH) * ny + oy0_me) * nxq * CH, es);
+            d.row_bytes = oy_me * nxq * CH * es;
+            d.src_pitch = d.row_bytes;
+            d.dst_pitch = ny * nxq * CH * es;
+            d.rows = int(zc / CH);
+            ps.push.push_back(d);
+            if (tail_here) {
+                PushDesc e{};
+                e.src = (const char*)eptr(slotp(SS, me), soff[q] + oy_me * nxq * nzm, es);
+                e.dst = (char*)eptr(slotp(D2, r), ny * nxq * nzm + oy0_me * rem, es);
+                e.row_bytes = oy_me * rem * es;
+                e.src_pitch = e.row_bytes;
+                e.dst_pitch = ny * rem * es;
+                e.rows = int(nxq);
+                ps.push.push_back(e);
+            }
+        }
+        {
+            const void* dd = nullptr;
+            if (T.upload(ps.push.data(), ps.push.size() * sizeof(PushDesc), &dd) != cudaSuccess) return fail(DFFT_ERR_CUDA, "push descriptors");
+            ps.push_d = (const PushDesc*)dd;
+        }
+        ps.record = ev_p[c] = nev++;
+        sc.steps.push_back(ps);
+    }
+    for (size_t c = 0; c < NSc; ++c) {
+        const size_t z0 = chunks.start[c], zc = chunks.size[c];
+        Step r = rendezvous(2, 2, 2);
+        r.waits.push_back(ev_p[c]);
+        sc.steps.push_back(r);
+        Step s;
+        rc = new_pass(PASS_C2C_TILED, ny, "y pass", s);
+        if (rc) return rc;
+        s.stream = 2;
+        s.prm.A0 = int(nx_p); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
+        s.prm.in = single_view(eptr(slotp(D2, me), (z0 / CH) * ny * nx_p * CH, es), (long long)CH, (long long)(ny * nx_p * CH), (long long)(nx_p * CH));
+        s.prm.out = single_view(eptr(slotp(D1, me), z0, es), (long long)(ny * nzc), (long long)CH, (long long)nzc);
+        s.prm.tile_swz = p->x_swz;
+        const bool tail_here = rem && c + 1 == NSc;
+        if (!tail_here) s.record = ev_y[c] = nev++;
+        sc.steps.push_back(s);
+        if (tail_here) {
+            Step t = s;
+            t.label = "y pass (tail)";
+            t.prm.A0 = int(nx_p); t.prm.A1 = 1; t.prm.B = int(rem);
+            t.prm.in = single_view(eptr(slotp(D2, me), ny * nx_p * nzm, es), (long long)(ny * rem), 0, (long long)rem);
+            t.prm.out = single_view(eptr(slotp(D1, me), nzm, es), (long long)(ny * nzc), 0, (long long)nzc);
+            t.record = ev_y[c] = nev++;
+            sc.steps.push_back(t);
+        }
+    }
+    Step s;
+    const PassKind zkind = c2c ? PASS_C2C_CONTIG : PASS_C2R;
+    const long long zpitch = c2c ? (long long)g.nz : (long long)(g.nz / 2);
+    rc = new_pass(zkind, c2c ? g.nz : g.nz / 2, c2c ? "z pass" : "z pass (C2R)", s);
+    if (rc) return rc;
+    s.prm.A0 = int(nx_p); s.prm.A1 = int(ny);
+    s.prm.in = single_view(slotp(D1, me), (long long)(ny * nzc), (long long)nzc, 1);
+    s.prm.out = single_view(nullptr, zpitch * (long long)ny, zpitch, 1);
+    s.out_user = 2;
+    s.stream = 0;
+    for (size_t c = 0; c < NSc; ++c) s.waits.push_back(ev_y[c]);
+    sc.steps.push_back(s);
     sc.nevents = nev;
     sc.built = true;
     return DFFT_SUCCESS;
@@ -1936,8 +2143,8 @@ static int get_schedule(dfft_plan_s* p, int inverse, int d, Schedule** out) {
                                          p->grp[1].size() > 1 && p->grp[2].size() > 1 && p->xchg_ctas >= 0 && pencil_overlap_enabled() && !seq_won;
         int rc;
         const int tst = p->tuned_staged[inverse ? 1 : 0];
-        const bool want_staged = want_overlap && !inverse && (tst >= 0 ? tst != 0 : p->staged != 0) && p->nslots >= 3 && p->blocked_ch > 0;
-        if (want_staged) { rc = build_staged_slab(p, sc); sc.staged = true; }
+        const bool want_staged = want_overlap && (tst >= 0 ? tst != 0 : p->staged != 0) && p->nslots >= 3 && p->blocked_ch > 0 && (!inverse || p->blocked_inv);
+        if (want_staged) { rc = inverse ? build_staged_slab_inverse(p, sc) : build_staged_slab(p, sc); sc.staged = true; }
         else if (want_overlap) rc = build_overlapped_slab(p, inverse ? 1 : 0, sc);
         else if (want_pencil_overlap) rc = build_overlapped_pencil(p, sc);
         else rc = build_schedule(p, inverse ? 1 : 0, d, sc);
@@ -2471,7 +2678,7 @@ int dfft_get_step_times(dfft_plan_t p, double* ms, int capacity) {
 // overwritten; the input is left intact.  Only plans created with send_method Streams have alternatives.
 static std::string cand_name(int seq, int ctas, int swap, int staged) {
     if (seq) return "sequential";
-    if (staged) return "overlapped/staged (local y pass + pusher)";
+    if (staged) return "overlapped/staged (local pass + " + std::to_string(ctas) + "-CTA pusher)";
     return "overlapped/" + (ctas > 0 ? std::to_string(ctas) + " CTAs" : std::string("full grid")) + (swap ? "/local passes first" : "");
 }
 int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int reps) {
@@ -2497,7 +2704,8 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
         // ... or at full size but outranked by them (the local passes take every CTA slot that frees up)
         for (int c : {0, sms}) cands.push_back({0, c, 1, 0});
         // ... or as a local pass whose output a small copy kernel pushes to the peers (slab forward)
-        if (p->g.decomp == DFFT_SLAB_ZY_THEN_X && !inverse && p->nslots >= 3 && p->blocked_ch > 0) cands.push_back({0, 0, 0, 1});
+        if (p->g.decomp == DFFT_SLAB_ZY_THEN_X && p->nslots >= 3 && p->blocked_ch > 0 && (!inverse || p->blocked_inv))
+            for (int c : {64, 128}) cands.push_back({0, c, 0, 1});  // ctas = CTAs of the pusher
     }
     p->tune_report.clear();
     if (cands.size() == 1) {
@@ -2517,6 +2725,7 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
         p->tuned_ctas[dir] = cands[k].seq ? -2 : cands[k].ctas;
         p->tuned_swap[dir] = cands[k].swap;
         p->tuned_staged[dir] = cands[k].staged;
+        p->tuned_push[dir] = cands[k].staged ? cands[k].ctas : 0;
         p->sched[dir][2] = Schedule();
         Schedule* sc = nullptr;
         int rc = get_schedule(p, inverse, 3, &sc);
@@ -2544,6 +2753,7 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
     p->tuned_ctas[dir] = cands[best].seq ? -2 : cands[best].ctas;
     p->tuned_swap[dir] = cands[best].swap;
     p->tuned_staged[dir] = cands[best].staged;
+    p->tuned_push[dir] = cands[best].staged ? cands[best].ctas : 0;
     p->sched[dir][2] = Schedule();
     p->timing = was_timing;
     cudaEventDestroy(e0);

@@ -42,6 +42,7 @@ def main():
                 par = d["config"].get("parity") or {}
                 print(name, "ms", round(d["ms_per_step"], 3), "inv_ms", round(d["config"]["ms_inverse"], 3), "GFLOP/s", round(d["value"]), "seq_ms", round(d["config"]["sequential_schedule_ms"], 3),
                       "parity", par.get("ok"), (par.get("small_grid") or {}).get("rel_l2_forward_max_over_ranks"),
+                      "tuned", d["config"].get("tuned_schedule"),
                       "steps", {k: round(v, 3) for k, v in r["steps_ms"].items()}, "nvlink", [x.get("gbs_per_direction") for x in (r["nvlink"] if isinstance(r.get("nvlink"), list) else [r.get("nvlink", {})])], flush=True)
         except (Exception, SystemExit) as ex:  # keep going: the box is expensive
             if rank == 0:

@@ -17,10 +17,8 @@ P1=2; P2=$((N/2))
 timeout 1500 $TR --master-port 29513 tools/multi_bench.py \
   "tuned:$B" \
   "sync:$B --send Sync" \
-  "streams_default:$B --no-tune" \
-  "streams_sms:$B --no-tune DFFT_XCHG_CTAS=148" \
-  "share4:$B --no-tune DFFT_XCHG_CTAS=148 DFFT_XCHG_WIDE=0 DFFT_BLOCKED=4 DFFT_X_SWZ=2" \
-  "share4_sync:$B --send Sync DFFT_XCHG_WIDE=0 DFFT_BLOCKED=4 DFFT_X_SWZ=2" \
+  "ovl98:$B --no-tune" \
+  "staged64:$B --no-tune DFFT_STAGED=1 DFFT_PUSH_CTAS=64" \
   "r2c_tuned:$B --transform r2c" \
   "r2c_sync:$B --transform r2c --send Sync" \
   "pencil_f32_sync:$B --decomp pencil --p1 $P1 --p2 $P2 --prec f32 --shape $PSHAPE --send Sync" \
@@ -29,7 +27,7 @@ timeout 1500 $TR --master-port 29513 tools/multi_bench.py \
   "pencil_f32_plain:$B --decomp pencil --p1 $P1 --p2 $P2 --prec f32 --shape $PSHAPE --send Sync DFFT_BLOCKED=0" \
   "a2a:$B --send Sync --comm All2All" \
   > gpurun_out/r02_mb${N}.log 2>&1; echo "multi_bench rc=$?"
-grep -v "^\[\|^\*\|^Setting\|NCCL version\|^$" gpurun_out/r02_mb${N}.log | cut -c1-420
+grep -v "^\[\|^\*\|^Setting\|NCCL version\|^$" gpurun_out/r02_mb${N}.log | cut -c1-1200
 # headline line with e2e (NUMA-local pinned buffers), as the driver runs it
 timeout 600 $TR --master-port 29514 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r02_bench_n${N}.json 2> gpurun_out/r02_bench_n${N}.err; echo "bench rc=$?"
 python - <<PY
