@@ -514,9 +514,15 @@ def main(argv=None):
     fft_ms = bd_avg["fft_ms"]
     tot_bytes = sum(q["algorithmic_bytes"] for q in passes)
     dom = max(passes, key=lambda q: q["ms"])
-    # DRAM bytes per launch of a pass, from the ncu --set full capture of exactly this launch shape
-    # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r01b_passes_n512_f64_ncu_full.csv): 2^27 f64 points
-    traffic = 2.1476e9 + 2.0993e9 if (f64 and c2c and int(ntot_local) == 2 ** 27 and world == 1) else None
+    # DRAM bytes per launch of the dominant pass, read from the committed ncu --set full capture of this workload
+    # (profiles/r02/bench_traffic.json, written from profiles/r02/ncu_full_final_kernels.csv); null for other workloads
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02", "bench_traffic.json")))
+        key = f"{shape[0]}x{shape[1]}x{shape[2]} {args.prec} {args.transform} {args.decomp} n{world}"
+        traffic = tj["workloads"].get(key, {}).get(dom["step"])
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["frac"], "traffic": traffic,
                 "peak_source": peak_src, "kernel": f"dominant FFT pass: {dom['step']} ({dom['ms']:.3f} ms per launch; algorithmic bytes = one read + one write of the local array)",
                 "all_passes": passes, "all_passes_achieved": tot_bytes / (fft_ms * 1e-3) / 1e9, "all_passes_frac": tot_bytes / (fft_ms * 1e-3) / 1e9 / hbm_peak,
@@ -550,12 +556,12 @@ def main(argv=None):
             cpu = {"value": flops_c2c(cs) / sec / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": desc, "ms": sec * 1e3,
                    "threads_effective": eff_par}
         ref = os.path.join(ROOT, "oracle", "_ref", "libcufft_ref.so")
-        if os.path.exists(ref) and c2c:
+        if os.path.exists(ref):
             try:
                 lib = C.CDLL(ref)
                 lib.cufft_ref_3d.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int]
                 msf = C.c_float()
-                if lib.cufft_ref_3d(1 if f64 else 0, 0, shape[0], shape[1], shape[2], out.data_ptr(), x.data_ptr(), C.byref(msf), 10) == 0:
+                if lib.cufft_ref_3d(1 if f64 else 0, 0 if c2c else 2, shape[0], shape[1], shape[2], out.data_ptr(), x.data_ptr(), C.byref(msf), 10) == 0:
                     cufft_ms = float(msf.value)
             except Exception:
                 cufft_ms = None

@@ -79,8 +79,10 @@ def build(verbose: bool = False, force: bool = False, defines=(), out: str = LIB
     lstamp = _stamp(objs)
     lfile = out + ".stamp"
     if not (os.path.exists(out) and os.path.exists(lfile) and open(lfile).read() == lstamp):
-        cmd = [NVCC, *ARCH, "-shared", "-o", out, *objs, "-lnccl", "-Xlinker", "-z,noexecstack"]
+        tmp = out + ".tmp"
+        cmd = [NVCC, *ARCH, "-shared", "-o", tmp, *objs, "-lnccl", "-Xlinker", "-z,noexecstack"]
         _run(cmd)
+        os.replace(tmp, out)  # atomic: a snapshot of the tree never sees a half-written library
         with open(lfile, "w") as f:
             f.write(lstamp)
     return out

@@ -333,6 +333,7 @@ struct dfft_plan_s {
     std::string tune_report;
     int ovl_groups = 4, ovl_chunks = 4;           // overlapped schedules: plane groups of the z pass, z chunks of the y / x passes
     int blocked_ch = 0;                           // > 0: slab forward keeps the y->x intermediate as [b/CH][Nx][CH]
+    int single_rank_layout = 1;                   // one rank: hand-over [ny][nzm/CH][nx][CH] (x innermost) instead of [nzm/CH][nx][ny][CH] (DFFT_N1_LAYOUT=0)
     int x_swz = 1;                                // tile-order blocking (log2 G) of passes that read the blocked hand-over layout
     int blocked_inv = 1;                          // the inverse x -> y hand-over is blocked as well (DFFT_BLOCKED_INV=0: plain)
     int xchg_tile_pref = 2;                       // tile preference of passes that store into other GPUs (2 = wide rows)
@@ -638,7 +639,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
             // the 1024-point f64 pass; measured 449 -> 700 GB/s per direction), locally the faster narrow one
             s2.prm.tile_pref = G2.size() > 1 ? p->xchg_tile_pref : 1;
             s2.prm.bulk_out = G2.size() > 1 ? p->bulk_store : 0;
-            if (G2.size() == 1) {
+            if (G2.size() == 1 && p->single_rank_layout) {
                 // one rank: keep x innermost, [ny][nzm/CH][nx][CH] — every x-pass tile is one contiguous block
                 // (measured 6254 GB/s for the 512-point x pass, profiles/r01_bench_n1.json)
                 s2.prm.out = single_view(slotp(D2, me), (long long)CH, (long long)(g.nx * CH), (long long)((nzm / CH) * g.nx * CH));
@@ -689,7 +690,7 @@ static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc) {
         if (CH) {
             // in: [nzc/CH][nx][oy_i][CH]: a0 = y_loc, a1 = z chunk, n = x
             s3.prm.A0 = int(oy_i); s3.prm.A1 = int(nzm / CH); s3.prm.B = int(CH);
-            if (G2.size() == 1)
+            if (G2.size() == 1 && p->single_rank_layout)
                 s3.prm.in = single_view(slotp(D2, me), (long long)((nzm / CH) * g.nx * CH), (long long)(g.nx * CH), (long long)CH);
             else
                 s3.prm.in = single_view(slotp(D2, me), (long long)CH, (long long)(g.nx * oy_i * CH), (long long)(oy_i * CH));
@@ -2422,6 +2423,7 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         const char* ew = getenv("DFFT_XCHG_WIDE");
         p->xchg_tile_pref = (ew && atoi(ew) == 0) ? 1 : 2;
         if (const char* ebi = getenv("DFFT_BLOCKED_INV")) p->blocked_inv = atoi(ebi) != 0;
+        if (const char* en1 = getenv("DFFT_N1_LAYOUT")) p->single_rank_layout = atoi(en1) != 0;
         if (const char* esw = getenv("DFFT_X_SWZ")) p->x_swz = std::max(0, std::min(4, atoi(esw)));
         const char* eb = getenv("DFFT_BLOCKED");
         // block width = the widest tile the y and x passes use for these lengths (fft_kernels.cuh: Shape::TBT —
@@ -2676,10 +2678,11 @@ int dfft_get_step_times(dfft_plan_t p, double* ms, int capacity) {
 // caller's buffers with each candidate — the sequential schedule and overlapped schedules with different numbers of
 // CTAs for the exchanging pass — and keeps the fastest one, judged by the slowest rank.  Collective; `out` is
 // overwritten; the input is left intact.  Only plans created with send_method Streams have alternatives.
-static std::string cand_name(int seq, int ctas, int swap, int staged) {
+static std::string cand_name(int seq, int ctas, int swap, int staged, int groups) {
     if (seq) return "sequential";
     if (staged) return "overlapped/staged (local pass + " + std::to_string(ctas) + "-CTA pusher)";
-    return "overlapped/" + (ctas > 0 ? std::to_string(ctas) + " CTAs" : std::string("full grid")) + (swap ? "/local passes first" : "");
+    return "overlapped/" + (ctas > 0 ? std::to_string(ctas) + " CTAs" : std::string("full grid")) + (swap ? "/local passes first" : "") +
+           (groups == 1 ? "/z pass unsplit" : "");
 }
 int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int reps) {
     if (!p) return fail(DFFT_ERR_INVALID, "null plan");
@@ -2690,9 +2693,10 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
     if (reps < 1) reps = 3;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->comm->device);
-    struct Cand { int seq; int ctas; int swap; int staged; };
+    struct Cand { int seq; int ctas; int swap; int staged; int groups; };  // groups: plane groups of the z pass (0 = the plan's default)
     std::vector<Cand> cands;
-    cands.push_back({1, 0, 0, 0});
+    cands.push_back({1, 0, 0, 0, 0});
+    const int groups_default = p->ovl_groups;
     const bool streams = p->cfg.send_method == DFFT_SEND_STREAMS || (p->g.decomp == DFFT_PENCIL && p->cfg.send_method2 == DFFT_SEND_STREAMS);
     const bool has_overlap = streams && p->P > 1 && p->xchg_ctas >= 0 &&
                              ((p->g.decomp == DFFT_SLAB_ZY_THEN_X && p->direct2) ||
@@ -2700,12 +2704,15 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
                                pencil_overlap_enabled()));
     if (has_overlap) {
         // exchange pass as a capped persistent grid that outranks the local passes ...
-        for (int c : {sms / 3, (2 * sms) / 3, sms, 2 * sms}) cands.push_back({0, c, 0, 0});
+        for (int c : {sms / 3, (2 * sms) / 3, sms, 2 * sms}) cands.push_back({0, c, 0, 0, 0});
+        // ... the same without splitting the z pass into plane groups (z alone at full speed, then y chunks | x chunks)
+        if (!inverse)
+            for (int c : {sms / 3, (2 * sms) / 3}) cands.push_back({0, c, 0, 0, 1});
         // ... or at full size but outranked by them (the local passes take every CTA slot that frees up)
-        for (int c : {0, sms}) cands.push_back({0, c, 1, 0});
+        for (int c : {0, sms}) cands.push_back({0, c, 1, 0, 0});
         // ... or as a local pass whose output a small copy kernel pushes to the peers (slab forward)
         if (p->g.decomp == DFFT_SLAB_ZY_THEN_X && p->nslots >= 3 && p->blocked_ch > 0 && (!inverse || p->blocked_inv))
-            for (int c : {64, 128}) cands.push_back({0, c, 0, 1});  // ctas = CTAs of the pusher
+            for (int c : {64, 128}) cands.push_back({0, c, 0, 1, 0});  // ctas = CTAs of the pusher
     }
     p->tune_report.clear();
     if (cands.size() == 1) {
@@ -2726,6 +2733,7 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
         p->tuned_swap[dir] = cands[k].swap;
         p->tuned_staged[dir] = cands[k].staged;
         p->tuned_push[dir] = cands[k].staged ? cands[k].ctas : 0;
+        if (!inverse) p->ovl_groups = cands[k].groups > 0 ? cands[k].groups : groups_default;
         p->sched[dir][2] = Schedule();
         Schedule* sc = nullptr;
         int rc = get_schedule(p, inverse, 3, &sc);
@@ -2746,7 +2754,7 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
         if (rc) return rc;
         double worst = 0;
         for (int r = 0; r < p->P; ++r) worst = std::max(worst, reinterpret_cast<const double*>(all.data())[r]);
-        rep += (k ? ", " : "") + cand_name(cands[k].seq, cands[k].ctas, cands[k].swap, cands[k].staged) + " " + std::to_string(worst).substr(0, 6) + " ms";
+        rep += (k ? ", " : "") + cand_name(cands[k].seq, cands[k].ctas, cands[k].swap, cands[k].staged, cands[k].groups) + " " + std::to_string(worst).substr(0, 6) + " ms";
         if (worst < best_ms) { best_ms = worst; best = int(k); }
     }
     p->tuned_seq[dir] = cands[best].seq;
@@ -2754,11 +2762,12 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
     p->tuned_swap[dir] = cands[best].swap;
     p->tuned_staged[dir] = cands[best].staged;
     p->tuned_push[dir] = cands[best].staged ? cands[best].ctas : 0;
+    if (!inverse) p->ovl_groups = cands[best].groups > 0 ? cands[best].groups : groups_default;
     p->sched[dir][2] = Schedule();
     p->timing = was_timing;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    p->tune_report = std::string(inverse ? "inverse: " : "forward: ") + rep + " -> " + cand_name(cands[best].seq, cands[best].ctas, cands[best].swap, cands[best].staged);
+    p->tune_report = std::string(inverse ? "inverse: " : "forward: ") + rep + " -> " + cand_name(cands[best].seq, cands[best].ctas, cands[best].swap, cands[best].staged, cands[best].groups);
     return best;
 }
 const char* dfft_plan_tune_report(dfft_plan_t p) { return p ? p->tune_report.c_str() : nullptr; }
