@@ -2423,6 +2423,9 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         const char* ew = getenv("DFFT_XCHG_WIDE");
         p->xchg_tile_pref = (ew && atoi(ew) == 0) ? 1 : 2;
         if (const char* ebi = getenv("DFFT_BLOCKED_INV")) p->blocked_inv = atoi(ebi) != 0;
+        // one rank: x innermost wins or ties up to 512-point y lines (2.01 ms either way at 512^3); for 1024-point y lines its far
+        // output rows cost the y pass 50 % (4.9 vs 3.2 ms at 1024^3 R2C, profiles/r02): use the general blocked layout there
+        p->single_rank_layout = ny < 1024 ? 1 : 0;
         if (const char* en1 = getenv("DFFT_N1_LAYOUT")) p->single_rank_layout = atoi(en1) != 0;
         if (const char* esw = getenv("DFFT_X_SWZ")) p->x_swz = std::max(0, std::min(4, atoi(esw)));
         const char* eb = getenv("DFFT_BLOCKED");

@@ -634,6 +634,12 @@ fft_c2c_tma_kernel(const __grid_constant__ FftParams p, const __grid_constant__ 
 }
 
 
+// complex value from another lane of the warp
+template <typename T>
+__device__ __forceinline__ cx<T> shfl_cx(cx<T> v, int src_lane) {
+    return cx<T>{__shfl_sync(0xffffffffu, v.x, src_lane), __shfl_sync(0xffffffffu, v.y, src_lane)};
+}
+
 // ---- R2C pass (CONTIG): real line of 2M points -> M+1 complex points ------------------------------------
 // The real line is read as M complex points z[m] = x[2m] + i x[2m+1], transformed with the length-M
 // core and split into even/odd spectra in shared memory:  X[k] = Xe[k] + W_2M^k Xo[k].
@@ -668,13 +674,40 @@ fft_r2c_kernel(const __grid_constant__ FftParams p) {
     }
     C::template stages<0>(v, j, t, sm, reinterpret_cast<const cx<T>*>(p.tw));
 
+    const cx<T>* tw2 = reinterpret_cast<const cx<T>*>(p.tw2);
+    if constexpr (TPL <= 32) {
+        // The line lives in one warp (TPL lanes): after the last stage thread j holds Z[j + e*TPL] in slot final_slot(e), and
+        // the partner Z[M - k] of k = j + e*TPL sits in lane TPL - j, slot final_slot(15 - e) (lane 0: its own slot
+        // final_slot(16 - e)).  The even / odd split therefore needs no shared memory: one shuffle per value instead of a
+        // store, a barrier and two loads (the reversed read order cost 25 % two-way bank conflicts).
+        //   X[k] = Xe + W_2M^k Xo,  Xe = (Z[k] + conj Z[M-k]) / 2,  Xo = -i (Z[k] - conj Z[M-k]) / 2,
+        //   W_2M^k = tw2[k] for k <= M/2 and -conj(tw2[M-k]) above.
+        const int lane = threadIdx.x & 31;
+        const int src = (lane & ~(TPL - 1)) + ((TPL - j) & (TPL - 1));
+        cx<T> z0 = v[C::Core::final_slot(0)];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const cx<T> zk = v[C::Core::final_slot(e)];
+            const cx<T> other = shfl_cx<T>(v[C::Core::final_slot(E - 1 - e)], src);
+            const cx<T> self = v[C::Core::final_slot((E - e) & (E - 1))];
+            const cx<T> zp = cconj(j == 0 ? self : other);
+            const int k = j + e * TPL;
+            const cx<T> xe = cx<T>{T(0.5) * (zk.x + zp.x), T(0.5) * (zk.y + zp.y)};
+            const cx<T> d = csub(zk, zp);
+            const cx<T> xo = cx<T>{T(0.5) * d.y, T(-0.5) * d.x};
+            cx<T> w;
+            if (2 * k <= M) w = ld_tw(tw2, k);
+            else { const cx<T> u = ld_tw(tw2, M - k); w = cx<T>{-u.x, u.y}; }
+            if (valid) st_elem<T>(out.at1(k), cadd(xe, cmul(w, xo)));
+        }
+        if (j == 0 && valid) st_elem<T>(out.at1(M), cx<T>{z0.x - z0.y, T(0)});
+    } else {
     // Z in natural order -> shared memory
     if constexpr (NST > 1) C::sync(t);
 #pragma unroll
     for (int e = 0; e < E; ++e) sm[C::sidx(j + e * TPL, t)] = v[C::Core::final_slot(e)];
     C::sync(t);
 
-    const cx<T>* tw2 = reinterpret_cast<const cx<T>*>(p.tw2);
     auto emit = [&](int k) {
         const int kk = (M - k) & (M - 1);
         const cx<T> zk = sm[C::sidx(k, t)], zp = cconj(sm[C::sidx(kk, t)]);
@@ -690,6 +723,7 @@ fft_r2c_kernel(const __grid_constant__ FftParams p) {
 #pragma unroll
     for (int e = 0; e < E / 2; ++e) emit(j + e * TPL);
     if (j == 0) emit(M / 2);
+    }
 }
 
 // ---- C2R pass (CONTIG): M+1 complex points -> real line of 2M points, unnormalised -----------------------
@@ -714,6 +748,39 @@ fft_c2r_kernel(const __grid_constant__ FftParams p) {
     const LA out(p.out, tab_out, t, tc.a0, tc.a1, 0);
 
     const cx<T>* tw2 = reinterpret_cast<const cx<T>*>(p.tw2);
+    cx<T> v[E];
+    if constexpr (TPL <= 32) {
+        // Mirror of the R2C split: thread j loads X[j + e*TPL] (coalesced), fetches the partners X[M - k] from lane TPL - j
+        // (slot E-1-e; lane 0: its own slot E-e, and X[M] for k = 0) with one shuffle each, and builds
+        //   Z[k] = (X[k] + conj X[M-k]) + i conj(W_2M^k) (X[k] - conj X[M-k])
+        // directly in the register layout the first stage expects — no staging through shared memory.
+        cx<T> xk[E];
+        cx<T> xM{T(0), T(0)};
+        if (valid) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) xk[e] = ld_elem<T>(in.at1(j + e * TPL));
+            if (j == 0) xM = ld_elem<T>(in.at1(M));
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) xk[e] = cx<T>{T(0), T(0)};
+        }
+        const int lane = threadIdx.x & 31;
+        const int src = (lane & ~(TPL - 1)) + ((TPL - j) & (TPL - 1));
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const cx<T> other = shfl_cx<T>(xk[E - 1 - e], src);
+            const cx<T> self = e == 0 ? xM : xk[(E - e) & (E - 1)];
+            const cx<T> xm = cconj(j == 0 ? self : other);
+            const int k = j + e * TPL;
+            cx<T> wc;  // conj(W_2M^k)
+            if (2 * k <= M) wc = cconj(ld_tw(tw2, k));
+            else { const cx<T> u = ld_tw(tw2, M - k); wc = cx<T>{-u.x, -u.y}; }
+            const cx<T> xe = cadd(xk[e], xm);
+            const cx<T> xo = cmul(wc, csub(xk[e], xm));
+            // stored with re/im swapped: the inverse transform is run as swap(fwd(swap(.)))
+            v[e] = cswap(cx<T>{xe.x - xo.y, xe.y + xo.x});
+        }
+    } else {
     // Z[k] = (X[k] + conj X[M-k]) + i * conj(W^k) * (X[k] - conj X[M-k]);  Z[M-k] = conj(Xe' - i Xo')
     auto build = [&](int k) {
         cx<T> xk{T(0), T(0)}, xm{T(0), T(0)};
@@ -731,9 +798,9 @@ fft_c2r_kernel(const __grid_constant__ FftParams p) {
     for (int e = 0; e < E / 2; ++e) build(j + e * TPL);
     if (j == 0) build(M / 2);
     C::sync(t);
-    cx<T> v[E];
     C::gather(v, sm, j, t);
     if constexpr (C::NST > 1) C::sync(t);
+    }
     C::template stages<0>(v, j, t, sm, reinterpret_cast<const cx<T>*>(p.tw));
     if (valid) {
         cx<T>* q = out.p0 + j;

@@ -124,18 +124,67 @@ def main(argv=None):
             back = torch.empty(isz, dtype=rdt, device="cuda")
             timed(lambda: plan.execC2R(back, buf, d))
     elif a.testcase == 1:
-        # distributed result == single 3D transform (the reference's coordinator runs cufftPlan3d; here the oracle)
-        if not small:
-            raise SystemExit("testcase 1 keeps the global array on every rank: use sizes up to 256^3")
-        xg = O.real_input(shape, dtype=npr)
-        ref = O.fft_r2c(xg, d)
-        x = torch.from_numpy(np.ascontiguousarray(O.block(xg, ist, isz))).cuda()
-        for _ in range(a.iterations):
-            plan.execR2C(out, x, d)
-        got = out[:n_out].cpu().numpy().reshape(osz)
-        blk = O.block(ref, ost, osz)
-        l1 = float(np.abs((got - blk).real).sum() + np.abs((got - blk).imag).sum())
-        rel = allmax(O.rel_l2(got, blk))
+        # distributed result == single 3D transform.  Small grids: against the numpy oracle on every rank.  Any size (the
+        # reference has no cap: random_dist_default.cu:300-371): rank 0 plays the reference's coordinator — it regenerates
+        # every rank's seeded block, runs cufftPlan3d on the global array (oracle/_ref/libcufft_ref.so) and compares each
+        # rank's output block, received over NCCL, on the device.
+        if small:
+            xg = O.real_input(shape, dtype=npr)
+            ref = O.fft_r2c(xg, d)
+            x = torch.from_numpy(np.ascontiguousarray(O.block(xg, ist, isz))).cuda()
+            for _ in range(a.iterations):
+                plan.execR2C(out, x, d)
+            got = out[:n_out].cpu().numpy().reshape(osz)
+            blk = O.block(ref, ost, osz)
+            l1 = float(np.abs((got - blk).real).sum() + np.abs((got - blk).imag).sum())
+            rel = allmax(O.rel_l2(got, blk))
+        else:
+            import ctypes as C
+            if d != 3:
+                raise SystemExit("testcase 1 above 256^3 compares with cufftPlan3d: full transforms only")
+            path = os.path.join(ROOT, "oracle", "_ref", "libcufft_ref.so")
+            if not os.path.exists(path):
+                raise SystemExit("testcase 1 above 256^3 needs oracle/_ref/libcufft_ref.so (make -C oracle)")
+            lib = C.CDLL(path)
+            lib.cufft_ref_3d.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int]
+
+            def gen(r, size):
+                return torch.rand(size, generator=torch.Generator(device="cuda").manual_seed(7000 + r), device="cuda", dtype=rdt) * 255
+            x = gen(rank, isz)
+            for _ in range(a.iterations):
+                plan.execR2C(out, x, d)
+            decomp = plan._decomp
+            p1_, p2_ = ((a.p1 or 1), (a.p2 or world // (a.p1 or 1))) if a.program == "pencil" else (world, 1)
+            acc = torch.zeros(3, device="cuda", dtype=torch.float64)  # sum |diff|^2, sum |ref|^2, sum |diff|_1
+            if rank == 0:
+                xg = torch.empty(shape, dtype=rdt, device="cuda")
+                for r in range(world):
+                    sz, st0 = dfft.layout(decomp, dfft.R2C, *shape, p1_, p2_, r, 0)
+                    xg[st0[0]:st0[0] + sz[0], st0[1]:st0[1] + sz[1], st0[2]:st0[2] + sz[2]] = x if r == 0 else gen(r, sz)
+                ref = torch.empty((a.nx, a.ny, a.nz // 2 + 1), dtype=cdt, device="cuda")
+                ms = C.c_float()
+                assert lib.cufft_ref_3d(1 if f64 else 0, 2, a.nx, a.ny, a.nz, ref.data_ptr(), xg.data_ptr(), C.byref(ms), 1) == 0
+                del xg
+                for r in range(world):
+                    sz, st0 = dfft.layout(decomp, dfft.R2C, *shape, p1_, p2_, r, 3)
+                    if r == 0:
+                        blk = out[:n_out].reshape(osz)
+                    else:
+                        blk = torch.empty(sz, dtype=cdt, device="cuda")
+                        dist.recv(torch.view_as_real(blk), src=r)
+                    rb = ref[st0[0]:st0[0] + sz[0], st0[1]:st0[1] + sz[1], st0[2]:st0[2] + sz[2]]
+                    step = max(1, (1 << 24) // (sz[1] * sz[2]))
+                    for i0 in range(0, sz[0], step):
+                        dd = blk[i0:i0 + step] - rb[i0:i0 + step]
+                        acc[0] += (dd.real.double() ** 2 + dd.imag.double() ** 2).sum()
+                        acc[1] += (rb[i0:i0 + step].real.double() ** 2 + rb[i0:i0 + step].imag.double() ** 2).sum()
+                        acc[2] += dd.real.double().abs().sum() + dd.imag.double().abs().sum()
+            else:
+                dist.send(torch.view_as_real(out[:n_out].reshape(osz).contiguous()), dst=0)
+            if world > 1:
+                dist.broadcast(acc, src=0)
+            rel = float((acc[0] / acc[1]).sqrt())
+            l1 = float(acc[2])
         if rank == 0:
             print(f"Result {l1}")
             print(f"Result (relative L2, max over ranks): {rel:.3e}  tolerance {tol:g}")

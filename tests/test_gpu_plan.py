@@ -315,6 +315,8 @@ def test_step_timeline():
     ["pencil", "-nx", "64", "-ny", "64", "-nz", "64", "-p1", "1", "-p2", "1", "-t", "4", "-d"],
     ["slab", "-nx", "64", "-ny", "64", "-nz", "64", "-t", "0", "-i", "2", "-w", "1"],
     ["slab", "-nx", "64", "-ny", "64", "-nz", "64", "-t", "2", "-d"],
+    ["slab", "-nx", "512", "-ny", "256", "-nz", "512", "-t", "1", "-d"],          # testcase 1 above 256^3: vs cufftPlan3d
+    ["pencil", "-nx", "256", "-ny", "512", "-nz", "512", "-p1", "1", "-p2", "1", "-t", "1"],
 ])
 def test_cli_testcases(argv, capsys):
     """The reference's CLI testcases 0-4 (tests/src/slab/main.cpp, tests/src/pencil/main.cpp) on one rank."""
