@@ -132,17 +132,6 @@ struct Tables {
         *out = (const unsigned char*)d;
         return e;
     }
-    // small device blobs owned by the schedules (push descriptors); freed with the segment tables
-    cudaError_t upload(const void* host, size_t nbytes, const void** out) {
-        if (dry || nbytes == 0) { *out = nullptr; return cudaSuccess; }
-        void* d = nullptr;
-        cudaError_t e = cudaMalloc(&d, nbytes);
-        if (e != cudaSuccess) return e;
-        e = cudaMemcpy(d, host, nbytes, cudaMemcpyHostToDevice);
-        bytes.push_back(d);
-        *out = d;
-        return e;
-    }
     // segment tables belong to the schedules: dropped whenever the schedules are rebuilt (dfft_set_work_area)
     void release_seg_tables() {
         for (void* p : bytes) cudaFree(p);
@@ -204,43 +193,6 @@ __global__ void rendezvous_kernel(unsigned long long* const* peer_flags, unsigne
 }
 
 
-// ---- staged exchange: the pusher -----------------------------------------------------------------------------
-// Copies strided runs of bytes from a local staging slot into the peers' slots (16-byte loads, 16-byte NVLink stores).
-// Pushing is cheap — 32 CTAs that do nothing else saturate the link (profiles/r02/nvlink_micro_push_rates.csv) — so the
-// exchanging FFT pass can run as a plain local pass at full speed while a few CTAs of this kernel move its output.
-struct PushDesc {
-    const char* src;
-    char* dst;
-    unsigned long long row_bytes, src_pitch, dst_pitch;  // multiples of 16
-    int rows, pad_;
-};
-constexpr int PUSH_PIECE = 32 * 1024;  // bytes one CTA moves per work item
-__global__ void __launch_bounds__(256) push_kernel(const PushDesc* descs, int ndesc) {
-    // work items: (descriptor, row, piece); enumerated identically by every CTA, taken round-robin
-    long long item = blockIdx.x;
-    long long base = 0;
-    for (int d = 0; d < ndesc; ++d) {
-        const PushDesc ds = descs[d];
-        const long long pieces = (long long)((ds.row_bytes + PUSH_PIECE - 1) / PUSH_PIECE);
-        const long long n = pieces * ds.rows;
-        for (; item < base + n; item += gridDim.x) {
-            const long long loc = item - base;
-            const long long row = loc / pieces, pc = loc % pieces;
-            const unsigned long long off = (unsigned long long)pc * PUSH_PIECE;
-            const unsigned long long len = ds.row_bytes - off < (unsigned long long)PUSH_PIECE ? ds.row_bytes - off : (unsigned long long)PUSH_PIECE;
-            const uint4* sp = reinterpret_cast<const uint4*>(ds.src + row * ds.src_pitch + off);
-            uint4* dp = reinterpret_cast<uint4*>(ds.dst + row * ds.dst_pitch + off);
-            const int n16 = int(len / 16);
-            uint4 r[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { const int i = threadIdx.x + k * 256; if (i < n16) r[k] = sp[i]; }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { const int i = threadIdx.x + k * 256; if (i < n16) dp[i] = r[k]; }
-        }
-        base += n;
-    }
-}
-
 }  // namespace dfft
 
 using namespace dfft;
@@ -253,7 +205,7 @@ struct dfft_comm_s {
 
 namespace dfft {
 
-enum StepType { STEP_PASS = 0, STEP_RENDEZVOUS = 1, STEP_A2A = 2, STEP_PUSH = 3 };
+enum StepType { STEP_PASS = 0, STEP_RENDEZVOUS = 1, STEP_A2A = 2 };
 
 struct Step {
     StepType type = STEP_PASS;
@@ -269,10 +221,6 @@ struct Step {
     // A2A
     std::vector<size_t> scount, soff, rcount, roff;  // elements, indexed by group member
     int send_slot = 0, recv_slot = 0;
-    // PUSH
-    std::vector<PushDesc> push;       // host copy
-    const PushDesc* push_d = nullptr; // device copy (Tables owns it)
-    int push_ctas = 32;
     // overlapped schedules: which plan stream runs the step (0 = caller's stream, 1 = exchange stream,
     // 2 = follow-up stream), events to wait for before it and the event to record after it
     int stream = 0;
@@ -284,8 +232,6 @@ struct Schedule {
     std::vector<Step> steps;
     bool built = false;
     bool overlapped = false;  // uses the plan's auxiliary streams
-    bool prio_swap = false;   // ... the pair in which the follow-up passes outrank the exchanging pass
-    bool staged = false;      // y pass local + push kernel (stream 3)
     int nevents = 0;
 };
 
@@ -318,17 +264,12 @@ struct dfft_plan_s {
     int* err_d = nullptr;
     unsigned long long epoch = 0;
     unsigned long long ticket[4] = {0, 0, 0, 0};  // per-phase rendezvous counters (same sequence on every rank)
-    cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};  // exchange (high priority), follow-up (low); swapped pair: exchange (low), follow-up (high)
-    int staged = 0;                               // overlapped slab forward uses the staged ("pusher") schedule (DFFT_STAGED)
-    int tuned_staged[2] = {-1, -1};
-    int tuned_push[2] = {0, 0};                   // dfft_plan_tune: CTAs of the pusher, per direction (0 = push_ctas)
-    int push_ctas = 32;                           // CTAs of the push kernel (DFFT_PUSH_CTAS)
-    int ovl_prio_swap = 0;                        // overlapped schedules use the swapped pair (DFFT_OVL_PRIO_SWAP)
-    int tuned_swap[2] = {-1, -1};                 // dfft_plan_tune: [fwd/inv] priority pair of the winning schedule (-1 = not tuned)
+    cudaStream_t aux[2] = {nullptr, nullptr};     // exchange stream (high priority), follow-up stream
     std::vector<cudaEvent_t> sync_events;
-    cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
     int xchg_ctas = 0;                            // SMs given to the exchange pass in overlapped schedules
     int tuned_seq[2] = {0, 0};                    // dfft_plan_tune: [fwd/inv] 1 = the sequential schedule won
+    int tuned_chunks[2] = {0, 0};                 // dfft_plan_tune: [fwd/inv] z chunks of the winning overlapped schedule (0 = ovl_chunks)
     int tuned_ctas[2] = {-2, -2};                 // dfft_plan_tune: [fwd/inv] exchange CTAs of the winning overlapped schedule (-2 = not tuned)
     std::string tune_report;
     int ovl_groups = 4, ovl_chunks = 4;           // overlapped schedules: plane groups of the z pass, z chunks of the y / x passes
@@ -390,8 +331,6 @@ namespace dfft {
 static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc);
 static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc);
 static int build_overlapped_pencil(dfft_plan_s* p, Schedule& sc);
-static int build_staged_slab(dfft_plan_s* p, Schedule& sc);
-static int build_staged_slab_inverse(dfft_plan_s* p, Schedule& sc);
 static bool pencil_overlap_enabled();
 
 }  // namespace dfft
@@ -1023,7 +962,8 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
     // plane groups (of my x planes) and z chunks
     Split groups, chunks;
     const size_t NG = std::min<size_t>(size_t(p->ovl_groups), nx_p);
-    const size_t NS = nzc >= 32 * size_t(p->ovl_chunks) ? size_t(p->ovl_chunks) : (nzc >= 32 ? 2 : 1);
+    const size_t want_chunks = size_t(p->tuned_chunks[inverse ? 1 : 0] > 0 ? p->tuned_chunks[inverse ? 1 : 0] : p->ovl_chunks);
+    const size_t NS = nzc >= 32 * want_chunks ? want_chunks : (nzc >= 32 ? 2 : 1);
     groups.make(nx_p, NG);
     const size_t CH = (inverse && !p->blocked_inv) ? 0 : size_t(p->blocked_ch);  // blocked hand-over, both directions
     const size_t rem = CH ? nzc % CH : 0, nzm = nzc - rem;
@@ -1314,7 +1254,8 @@ static int build_overlapped_pencil(dfft_plan_s* p, Schedule& sc) {
     for (size_t v : g.sx.size) min_nx = std::min(min_nx, v);
     for (size_t v : g.sz.size) min_nz = std::min(min_nz, v);
     const size_t NG = std::min<size_t>(size_t(p->ovl_groups), min_nx);
-    const size_t NS = min_nz >= 32 * size_t(p->ovl_chunks) ? size_t(p->ovl_chunks) : (min_nz >= 32 ? 2 : 1);
+    const size_t want_chunks = size_t(p->tuned_chunks[0] > 0 ? p->tuned_chunks[0] : p->ovl_chunks);
+    const size_t NS = min_nz >= 32 * want_chunks ? want_chunks : (min_nz >= 32 ? 2 : 1);
     Split groups, chunks;
     groups.make(nx_i, NG);
     // blocked hand-over of the second transposition: receiver (q, j) holds [nz_j/CH][nx][ny_q][CH] (+ a plain-layout
@@ -1447,422 +1388,6 @@ static int build_overlapped_pencil(dfft_plan_s* p, Schedule& sc) {
 
 }  // namespace dfft
 
-
-namespace dfft {
-
-// Staged overlapped slab schedule (ZY_Then_X, forward, Peer2Peer, SendMethod Streams) — "the pusher".
-//
-// The fused schedules let the y pass itself store into the peers.  That pass then runs at link speed (2.7 ms for 2 GiB at
-// 8 GPUs) although its FFT work is worth 0.9 ms of the GPU, and it occupies the SMs it was given while it waits for the
-// link.  Here the y pass is a plain local pass again: it writes its output, already in the receivers' blocked layout,
-// into a local staging slot (the own block goes straight into the own receive slot), and a small persistent copy
-// kernel — `push_ctas` CTAs, no shared memory, 40 registers — moves the staged blocks into the peers' slots on a
-// high-priority stream.  Cost: one extra write + read of the exchanged data in local HBM; gain: the link is driven at
-// its ceiling by a handful of CTAs while all SMs keep doing FFT work.
-//   stream 0: z pass per plane group
-//   stream 1: y pass per (z chunk, plane group), local, full grid
-//   stream 3: push per (z chunk, plane group), high priority
-//   stream 2: per z chunk: rendezvous with the peers, x pass of that chunk
-static int build_staged_slab(dfft_plan_s* p, Schedule& sc) {
-    const Geometry& g = p->g;
-    const int me = p->rank;
-    const size_t es = p->esize;
-    const bool c2c = g.transform == DFFT_C2C;
-    Tables& T = p->tabs;
-    sc.steps.clear();
-    sc.overlapped = true;
-    const size_t nzc = g.nzc, ny = g.ny, nx = g.nx;
-    const size_t nx_p = g.sx.size[me], x0 = g.sx.start[me];
-    const size_t oy_me = g.oy.size[me];
-    const std::vector<int>& G2 = p->grp[2];
-    const int D1 = 0, D2 = 1, SS = 2;
-    if (p->nslots < 3) return fail(DFFT_ERR_STATE, "internal: staged schedule needs a staging slot");
-    auto slotp = [&](int s_, int r) -> void* { return p->slot_ptr[s_][r]; };
-    int nev = 0;
-    const size_t CH = size_t(p->blocked_ch);
-    if (!CH) return fail(DFFT_ERR_STATE, "internal: staged schedule needs the blocked hand-over layout");
-    const size_t rem = nzc % CH, nzm = nzc - rem;
-
-    auto new_pass = [&](PassKind kind, size_t n, const char* label, Step& s) -> int {
-        s = Step();
-        s.type = STEP_PASS;
-        s.kind = kind;
-        s.label = label;
-        s.log2n = ilog2_exact(n);
-        if (s.log2n < 1 || s.log2n > MAX_LOG2N) return fail(DFFT_ERR_UNSUPPORTED, "unsupported axis length");
-        s.prm.A0 = 1; s.prm.A1 = 1; s.prm.B = 1;
-        s.prm.inverse = 0;
-        void* tw = nullptr;
-        if (T.get_tw(s.log2n, &tw) != cudaSuccess) return fail(DFFT_ERR_CUDA, "twiddle table allocation failed");
-        s.prm.tw = tw;
-        if (kind == PASS_R2C) {
-            void* tw2 = nullptr;
-            if (T.get_tw2(s.log2n, &tw2) != cudaSuccess) return fail(DFFT_ERR_CUDA, "twiddle table allocation failed");
-            s.prm.tw2 = tw2;
-        }
-        return DFFT_SUCCESS;
-    };
-    auto rendezvous = [&](int group, int phase_id, int stream) {
-        Step s;
-        s.type = STEP_RENDEZVOUS;
-        s.label = group == 0 ? "entry rendezvous" : "rendezvous 2";
-        s.group = group;
-        s.phase_id = phase_id;
-        s.stream = stream;
-        return s;
-    };
-
-    Split groups, chunks;
-    const size_t NG = std::min<size_t>(size_t(p->ovl_groups), nx_p);
-    const size_t NSw = nzc >= 32 * size_t(p->ovl_chunks) ? size_t(p->ovl_chunks) : (nzc >= 32 ? 2 : 1);
-    groups.make(nx_p, NG);
-    {
-        Split u;
-        u.make(nzm / CH, std::min<size_t>(NSw, nzm / CH));
-        for (size_t c = 0; c < u.size.size(); ++c) { chunks.size.push_back(u.size[c] * CH); chunks.start.push_back(u.start[c] * CH); }
-    }
-    const size_t NSc = chunks.size.size();
-    const unsigned char* tab_y = nullptr;
-    if (T.seg_table(g.oy, &tab_y) != cudaSuccess) return fail(DFFT_ERR_CUDA, "segment table");
-    // staging slot: per destination q a region [nzm/CH][nx_p][ny_q][CH] followed by its tail [nx_p][ny_q][rem]
-    std::vector<size_t> soff(G2.size(), 0);
-    {
-        size_t o = 0;
-        for (size_t q = 0; q < G2.size(); ++q) { soff[q] = o; o += nx_p * g.oy.size[q] * nzc; }
-    }
-
-    sc.steps.push_back(rendezvous(0, 0, 0));  // everyone has left the previous exec: receive slots may be overwritten
-    const int ev_entry = nev++;
-    sc.steps.back().record = ev_entry;
-    int rc;
-    std::vector<int> ev_z(NG), ev_p(NSc);
-    for (size_t gi = 0; gi < NG; ++gi) {
-        Step s;
-        rc = new_pass(c2c ? PASS_C2C_CONTIG : PASS_R2C, c2c ? g.nz : g.nz / 2, c2c ? "z pass" : "z pass (R2C)", s);
-        if (rc) return rc;
-        const size_t pl0 = groups.start[gi], npl = groups.size[gi];
-        const long long pitch = c2c ? (long long)g.nz : (long long)(g.nz / 2);
-        s.prm.A0 = int(npl); s.prm.A1 = int(ny);
-        s.prm.in = single_view((void*)(size_t)(pl0 * ny * pitch * es), pitch * (long long)ny, pitch, 1);
-        s.in_user = 1;
-        s.prm.out = single_view(eptr(slotp(D1, me), pl0 * ny * nzc, es), (long long)(ny * nzc), (long long)nzc, 1);
-        s.stream = 0;
-        s.record = ev_z[gi] = nev++;
-        sc.steps.push_back(s);
-    }
-    for (size_t c = 0; c < NSc; ++c) {
-        const size_t z0 = chunks.start[c], zc = chunks.size[c];
-        const bool last_chunk = c + 1 == NSc;
-        for (size_t gi = 0; gi < NG; ++gi) {
-            const size_t pl0 = groups.start[gi], npl = groups.size[gi];
-            Step s;
-            rc = new_pass(PASS_C2C_TILED, ny, "y pass", s);
-            if (rc) return rc;
-            s.prm.A0 = int(npl); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
-            s.prm.in = single_view(eptr(slotp(D1, me), pl0 * ny * nzc + z0, es), (long long)(ny * nzc), (long long)CH, (long long)nzc);
-            s.prm.tile_pref = 0;
-            seg_view(s.prm.out, tab_y, G2, [&](int q, int r) {
-                const size_t nyq = g.oy.size[q];
-                if (r == me)  // own block: straight into the own receive slot
-                    return mkseg(eptr(slotp(D2, me), ((z0 / CH) * nx + x0 + pl0) * nyq * CH, es), (long long)(nyq * CH), (long long)(nx * nyq * CH),
-                                 (long long)CH, g.oy.start[q]);
-                return mkseg(eptr(slotp(SS, me), soff[q] + ((z0 / CH) * nx_p + pl0) * nyq * CH, es), (long long)(nyq * CH), (long long)(nx_p * nyq * CH),
-                             (long long)CH, g.oy.start[q]);
-            });
-            s.stream = 1;
-            if (c == 0) s.waits.push_back(ev_z[gi]);
-            if (c == 0 && gi == 0) s.waits.push_back(ev_entry);
-            const int ev_y = nev++;
-            const bool tail_here = rem && last_chunk;
-            if (!tail_here) s.record = ev_y;
-            sc.steps.push_back(s);
-            if (tail_here) {
-                Step t = s;
-                t.label = "y pass (tail)";
-                t.waits.clear();
-                t.prm.A0 = int(npl); t.prm.A1 = 1; t.prm.B = int(rem);
-                t.prm.in = single_view(eptr(slotp(D1, me), pl0 * ny * nzc + nzm, es), (long long)(ny * nzc), 0, (long long)nzc);
-                seg_view(t.prm.out, tab_y, G2, [&](int q, int r) {
-                    const size_t nyq = g.oy.size[q];
-                    if (r == me) return mkseg(eptr(slotp(D2, me), nx * nyq * nzm + (x0 + pl0) * nyq * rem, es), (long long)(nyq * rem), 0, (long long)rem, g.oy.start[q]);
-                    return mkseg(eptr(slotp(SS, me), soff[q] + nx_p * nyq * nzm + pl0 * nyq * rem, es), (long long)(nyq * rem), 0, (long long)rem, g.oy.start[q]);
-                });
-                t.record = ev_y;
-                sc.steps.push_back(t);
-            }
-            // push (c, gi): staged blocks -> the peers' receive slots
-            Step ps;
-            ps.type = STEP_PUSH;
-            ps.label = "push";
-            ps.stream = 3;
-            ps.push_ctas = p->tuned_push[0] > 0 ? p->tuned_push[0] : p->push_ctas;
-            ps.waits.push_back(ev_y);
-            for (size_t q = 0; q < G2.size(); ++q) {
-                const int r = G2[q];
-                if (r == me) continue;
-                const size_t nyq = g.oy.size[q];
-                PushDesc d{};
-                d.src = (const char*)eptr(slotp(SS, me), soff[q] + ((z0 / CH) * nx_p + pl0) * nyq * CH, es);
-                d.dst = (char*)eptr(slotp(D2, r), ((z0 / CH) * nx + x0 + pl0) * nyq * CH, es);
-                d.row_bytes = npl * nyq * CH * es;
-                d.src_pitch = nx_p * nyq * CH * es;
-                d.dst_pitch = nx * nyq * CH * es;
-                d.rows = int(zc / CH);
-                ps.push.push_back(d);
-                if (tail_here) {
-                    PushDesc e{};
-                    e.src = (const char*)eptr(slotp(SS, me), soff[q] + nx_p * nyq * nzm + pl0 * nyq * rem, es);
-                    e.dst = (char*)eptr(slotp(D2, r), nx * nyq * nzm + (x0 + pl0) * nyq * rem, es);
-                    e.row_bytes = npl * nyq * rem * es;
-                    e.src_pitch = e.dst_pitch = e.row_bytes;
-                    e.rows = 1;
-                    ps.push.push_back(e);
-                }
-            }
-            {
-                const void* dd = nullptr;
-                if (T.upload(ps.push.data(), ps.push.size() * sizeof(PushDesc), &dd) != cudaSuccess) return fail(DFFT_ERR_CUDA, "push descriptors");
-                ps.push_d = (const PushDesc*)dd;
-            }
-            if (gi + 1 == NG) ps.record = ev_p[c] = nev++;
-            sc.steps.push_back(ps);
-        }
-    }
-    for (size_t c = 0; c < NSc; ++c) {
-        const size_t z0 = chunks.start[c], zc = chunks.size[c];
-        Step r = rendezvous(2, 2, 2);
-        r.waits.push_back(ev_p[c]);
-        sc.steps.push_back(r);
-        Step s;
-        rc = new_pass(PASS_C2C_TILED, nx, "x pass", s);
-        if (rc) return rc;
-        s.prm.A0 = int(oy_me); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
-        s.prm.in = single_view(eptr(slotp(D2, me), (z0 / CH) * nx * oy_me * CH, es), (long long)CH, (long long)(nx * oy_me * CH), (long long)(oy_me * CH));
-        s.prm.out = single_view((void*)(size_t)(z0 * es), (long long)nzc, (long long)CH, (long long)(oy_me * nzc));
-        s.prm.tile_swz = p->x_swz;
-        s.out_user = 2;
-        s.stream = 2;
-        sc.steps.push_back(s);
-        if (rem && c + 1 == NSc) {
-            Step t = s;
-            t.label = "x pass (tail)";
-            t.prm.A0 = int(oy_me); t.prm.A1 = 1; t.prm.B = int(rem);
-            t.prm.in = single_view(eptr(slotp(D2, me), nx * oy_me * nzm, es), (long long)rem, 0, (long long)(oy_me * rem));
-            t.prm.out = single_view((void*)(size_t)(nzm * es), (long long)nzc, 0, (long long)(oy_me * nzc));
-            sc.steps.push_back(t);
-        }
-    }
-    sc.nevents = nev;
-    sc.built = true;
-    return DFFT_SUCCESS;
-}
-
-}  // namespace dfft
-
-
-namespace dfft {
-
-// Staged overlapped slab schedule, inverse: x pass per z chunk as a local pass into the staging slot (receivers' blocked
-// layout [nzc/CH][ny][nx_q][CH], own block straight into the own slot), pusher, then per chunk rendezvous + y pass, z pass last.
-static int build_staged_slab_inverse(dfft_plan_s* p, Schedule& sc) {
-    const Geometry& g = p->g;
-    const int me = p->rank;
-    const size_t es = p->esize;
-    const bool c2c = g.transform == DFFT_C2C;
-    Tables& T = p->tabs;
-    sc.steps.clear();
-    sc.overlapped = true;
-    const size_t nzc = g.nzc, ny = g.ny, nx = g.nx;
-    const size_t nx_p = g.sx.size[me];
-    const size_t oy_me = g.oy.size[me], oy0_me = g.oy.start[me];
-    const std::vector<int>& G2 = p->grp[2];
-    const int D1 = 0, D2 = 1, SS = 2;
-    if (p->nslots < 3) return fail(DFFT_ERR_STATE, "internal: staged schedule needs a staging slot");
-    auto slotp = [&](int s_, int r) -> void* { return p->slot_ptr[s_][r]; };
-    int nev = 0;
-    const size_t CH = size_t(p->blocked_ch);
-    if (!CH) return fail(DFFT_ERR_STATE, "internal: staged schedule needs the blocked hand-over layout");
-    const size_t rem = nzc % CH, nzm = nzc - rem;
-    (void)nx;
-
-    auto new_pass = [&](PassKind kind, size_t n, const char* label, Step& s) -> int {
-        s = Step();
-        s.type = STEP_PASS;
-        s.kind = kind;
-        s.label = label;
-        s.log2n = ilog2_exact(n);
-        if (s.log2n < 1 || s.log2n > MAX_LOG2N) return fail(DFFT_ERR_UNSUPPORTED, "unsupported axis length");
-        s.prm.A0 = 1; s.prm.A1 = 1; s.prm.B = 1;
-        s.prm.inverse = 1;
-        void* tw = nullptr;
-        if (T.get_tw(s.log2n, &tw) != cudaSuccess) return fail(DFFT_ERR_CUDA, "twiddle table allocation failed");
-        s.prm.tw = tw;
-        if (kind == PASS_C2R) {
-            void* tw2 = nullptr;
-            if (T.get_tw2(s.log2n, &tw2) != cudaSuccess) return fail(DFFT_ERR_CUDA, "twiddle table allocation failed");
-            s.prm.tw2 = tw2;
-        }
-        return DFFT_SUCCESS;
-    };
-    auto rendezvous = [&](int group, int phase_id, int stream) {
-        Step s;
-        s.type = STEP_RENDEZVOUS;
-        s.label = group == 0 ? "entry rendezvous" : "rendezvous 2";
-        s.group = group;
-        s.phase_id = phase_id;
-        s.stream = stream;
-        return s;
-    };
-
-    Split chunks;
-    const size_t NSw = nzc >= 32 * size_t(p->ovl_chunks) ? size_t(p->ovl_chunks) : (nzc >= 32 ? 2 : 1);
-    {
-        Split u;
-        u.make(nzm / CH, std::min<size_t>(NSw, nzm / CH));
-        for (size_t c = 0; c < u.size.size(); ++c) { chunks.size.push_back(u.size[c] * CH); chunks.start.push_back(u.start[c] * CH); }
-    }
-    const size_t NSc = chunks.size.size();
-    const unsigned char* tab_x = nullptr;
-    if (T.seg_table(g.sx, &tab_x) != cudaSuccess) return fail(DFFT_ERR_CUDA, "segment table");
-    // staging slot: per destination q a region [nzm/CH][oy_me][nx_q][CH] followed by its tail [nx_q][oy_me][rem]
-    std::vector<size_t> soff(G2.size(), 0);
-    {
-        size_t o = 0;
-        for (size_t q = 0; q < G2.size(); ++q) { soff[q] = o; o += oy_me * g.sx.size[q] * nzc; }
-    }
-
-    sc.steps.push_back(rendezvous(0, 0, 0));
-    const int ev_entry = nev++;
-    sc.steps.back().record = ev_entry;
-    int rc;
-    std::vector<int> ev_p(NSc), ev_y(NSc);
-    for (size_t c = 0; c < NSc; ++c) {
-        const size_t z0 = chunks.start[c], zc = chunks.size[c];
-        const bool tail_here = rem && c + 1 == NSc;
-        Step s;
-        rc = new_pass(PASS_C2C_TILED, nx, "x pass", s);
-        if (rc) return rc;
-        s.in_user = 1;
-        s.prm.A0 = int(oy_me); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
-        s.prm.in = single_view((void*)(size_t)(z0 * es), (long long)nzc, (long long)CH, (long long)(oy_me * nzc));
-        seg_view(s.prm.out, tab_x, G2, [&](int q, int r) {
-            const size_t nxq = g.sx.size[q];
-            if (r == me)
-                return mkseg(eptr(slotp(D2, me), ((z0 / CH) * ny + oy0_me) * nxq * CH, es), (long long)(nxq * CH), (long long)(ny * nxq * CH), (long long)CH, g.sx.start[q]);
-            return mkseg(eptr(slotp(SS, me), soff[q] + (z0 / CH) * oy_me * nxq * CH, es), (long long)(nxq * CH), (long long)(oy_me * nxq * CH), (long long)CH, g.sx.start[q]);
-        });
-        s.stream = 1;
-        if (c == 0) s.waits.push_back(ev_entry);
-        const int ev_x = nev++;
-        if (!tail_here) s.record = ev_x;
-        sc.steps.push_back(s);
-        if (tail_here) {
-            Step t = s;
-            t.label = "x pass (tail)";
-            t.waits.clear();
-            t.prm.A0 = int(oy_me); t.prm.A1 = 1; t.prm.B = int(rem);
-            t.prm.in = single_view((void*)(size_t)(nzm * es), (long long)nzc, 0, (long long)(oy_me * nzc));
-            // every segment of a view shares one stride along x: the own tail block is staged as well and copied by the pusher
-            seg_view(t.prm.out, tab_x, G2, [&](int q, int) {
-                const size_t nxq = g.sx.size[q];
-                return mkseg(eptr(slotp(SS, me), soff[q] + oy_me * nxq * nzm, es), (long long)rem, 0, (long long)(oy_me * rem), g.sx.start[q]);
-            });
-            t.record = ev_x;
-            sc.steps.push_back(t);
-        }
-        Step ps;
-        ps.type = STEP_PUSH;
-        ps.label = "push";
-        ps.stream = 3;
-        ps.push_ctas = p->tuned_push[1] > 0 ? p->tuned_push[1] : p->push_ctas;
-        ps.waits.push_back(ev_x);
-        for (size_t q = 0; q < G2.size(); ++q) {
-            const int r = G2[q];
-            const size_t nxq = g.sx.size[q];
-            if (r == me) {
-                if (tail_here) {  // own tail block: staging -> own slot (local copy)
-                    PushDesc e{};
-                    e.src = (const char*)eptr(slotp(SS, me), soff[q] + oy_me * nxq * nzm, es);
-                    e.dst = (char*)eptr(slotp(D2, me), ny * nxq * nzm + oy0_me * rem, es);
-                    e.row_bytes = oy_me * rem * es;
-                    e.src_pitch = e.row_bytes;
-                    e.dst_pitch = ny * rem * es;
-                    e.rows = int(nxq);
-                    ps.push.push_back(e);
-                }
-                continue;
-            }
-            PushDesc d{};
-            d.src = (const char*)eptr(slotp(SS, me), soff[q] + (z0 / CH) * oy_me * nxq * CH, es);
-            d.dst = (char*)eptr(slotp(D2, r), ((z0 / CH) * ny + oy0_me) * nxq * CH, es);
-            d.row_bytes = oy_me * nxq * CH * es;
-            d.src_pitch = d.row_bytes;
-            d.dst_pitch = ny * nxq * CH * es;
-            d.rows = int(zc / CH);
-            ps.push.push_back(d);
-            if (tail_here) {
-                PushDesc e{};
-                e.src = (const char*)eptr(slotp(SS, me), soff[q] + oy_me * nxq * nzm, es);
-                e.dst = (char*)eptr(slotp(D2, r), ny * nxq * nzm + oy0_me * rem, es);
-                e.row_bytes = oy_me * rem * es;
-                e.src_pitch = e.row_bytes;
-                e.dst_pitch = ny * rem * es;
-                e.rows = int(nxq);
-                ps.push.push_back(e);
-            }
-        }
-        {
-            const void* dd = nullptr;
-            if (T.upload(ps.push.data(), ps.push.size() * sizeof(PushDesc), &dd) != cudaSuccess) return fail(DFFT_ERR_CUDA, "push descriptors");
-            ps.push_d = (const PushDesc*)dd;
-        }
-        ps.record = ev_p[c] = nev++;
-        sc.steps.push_back(ps);
-    }
-    for (size_t c = 0; c < NSc; ++c) {
-        const size_t z0 = chunks.start[c], zc = chunks.size[c];
-        Step r = rendezvous(2, 2, 2);
-        r.waits.push_back(ev_p[c]);
-        sc.steps.push_back(r);
-        Step s;
-        rc = new_pass(PASS_C2C_TILED, ny, "y pass", s);
-        if (rc) return rc;
-        s.stream = 2;
-        s.prm.A0 = int(nx_p); s.prm.A1 = int(zc / CH); s.prm.B = int(CH);
-        s.prm.in = single_view(eptr(slotp(D2, me), (z0 / CH) * ny * nx_p * CH, es), (long long)CH, (long long)(ny * nx_p * CH), (long long)(nx_p * CH));
-        s.prm.out = single_view(eptr(slotp(D1, me), z0, es), (long long)(ny * nzc), (long long)CH, (long long)nzc);
-        s.prm.tile_swz = p->x_swz;
-        const bool tail_here = rem && c + 1 == NSc;
-        if (!tail_here) s.record = ev_y[c] = nev++;
-        sc.steps.push_back(s);
-        if (tail_here) {
-            Step t = s;
-            t.label = "y pass (tail)";
-            t.prm.A0 = int(nx_p); t.prm.A1 = 1; t.prm.B = int(rem);
-            t.prm.in = single_view(eptr(slotp(D2, me), ny * nx_p * nzm, es), (long long)(ny * rem), 0, (long long)rem);
-            t.prm.out = single_view(eptr(slotp(D1, me), nzm, es), (long long)(ny * nzc), 0, (long long)nzc);
-            t.record = ev_y[c] = nev++;
-            sc.steps.push_back(t);
-        }
-    }
-    Step s;
-    const PassKind zkind = c2c ? PASS_C2C_CONTIG : PASS_C2R;
-    const long long zpitch = c2c ? (long long)g.nz : (long long)(g.nz / 2);
-    rc = new_pass(zkind, c2c ? g.nz : g.nz / 2, c2c ? "z pass" : "z pass (C2R)", s);
-    if (rc) return rc;
-    s.prm.A0 = int(nx_p); s.prm.A1 = int(ny);
-    s.prm.in = single_view(slotp(D1, me), (long long)(ny * nzc), (long long)nzc, 1);
-    s.prm.out = single_view(nullptr, zpitch * (long long)ny, zpitch, 1);
-    s.out_user = 2;
-    s.stream = 0;
-    for (size_t c = 0; c < NSc; ++c) s.waits.push_back(ev_y[c]);
-    sc.steps.push_back(s);
-    sc.nevents = nev;
-    sc.built = true;
-    return DFFT_SUCCESS;
-}
-
-}  // namespace dfft
 
 // =====================================================================================================
 // memory / peer mapping
@@ -2017,10 +1542,8 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
     int launches = 0;
     int ev = 0;
     const bool timing = p->timing;
-    // aux[0] high, aux[1] low, aux[2] low, aux[3] high priority
-    cudaStream_t ax0 = sc.prio_swap ? p->aux[2] : p->aux[0], ax1 = sc.prio_swap ? p->aux[3] : p->aux[1], ax2 = nullptr;
-    if (sc.staged) { ax0 = p->aux[1]; ax1 = p->aux[2]; ax2 = p->aux[0]; }  // y and x passes at low priority, the pusher above them
-    cudaStream_t streams[4] = {st, ax0, ax1, ax2};
+    cudaStream_t const ax0 = p->aux[0], ax1 = p->aux[1];
+    cudaStream_t streams[3] = {st, ax0, ax1};
     auto mark = [&](const char* name, int is_fft, const char* label = "") -> cudaError_t {
         if (!timing || (sc.overlapped && is_fft != -1)) return cudaSuccess;  // overlapped: only start / end are meaningful
         if (ev >= int(p->events.size())) {
@@ -2046,7 +1569,6 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
         CK_CUDA(cudaEventRecord(p->fork_ev, st));
         CK_CUDA(cudaStreamWaitEvent(ax0, p->fork_ev, 0));
         CK_CUDA(cudaStreamWaitEvent(ax1, p->fork_ev, 0));
-        if (ax2) CK_CUDA(cudaStreamWaitEvent(ax2, p->fork_ev, 0));
     }
     CK_CUDA(mark("start", -1));
     int tl = 0;
@@ -2077,13 +1599,6 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
             if (e != cudaSuccess) return fail(DFFT_ERR_CUDA, std::string("FFT pass launch failed: ") + cudaGetErrorString(e));
             ++launches;
             CK_CUDA(mark(s.phase, 1, s.label));
-        } else if (s.type == STEP_PUSH) {
-            if (!s.push.empty()) {
-                push_kernel<<<s.push_ctas, 256, 0, ss>>>(s.push_d, int(s.push.size()));
-                CK_CUDA(cudaGetLastError());
-                ++launches;
-            }
-            CK_CUDA(mark(s.phase, 0, s.label));
         } else if (s.type == STEP_RENDEZVOUS) {
             const std::vector<int>& G = p->grp[s.group];
             if (G.size() > 1) {
@@ -2119,10 +1634,6 @@ static int run_schedule(dfft_plan_s* p, Schedule& sc, void* out, const void* in,
             CK_CUDA(cudaEventRecord(p->join_ev[a], a == 0 ? ax0 : ax1));
             CK_CUDA(cudaStreamWaitEvent(st, p->join_ev[a], 0));
         }
-        if (ax2) {
-            CK_CUDA(cudaEventRecord(p->join_ev[2], ax2));
-            CK_CUDA(cudaStreamWaitEvent(st, p->join_ev[2], 0));
-        }
     }
     CK_CUDA(mark("Run complete", -1));
     if (timing) p->n_events_used = ev;
@@ -2143,16 +1654,11 @@ static int get_schedule(dfft_plan_s* p, int inverse, int d, Schedule** out) {
         const bool want_pencil_overlap = streams && d == 3 && !inverse && p->g.decomp == DFFT_PENCIL && p->direct1 && p->direct2 &&
                                          p->grp[1].size() > 1 && p->grp[2].size() > 1 && p->xchg_ctas >= 0 && pencil_overlap_enabled() && !seq_won;
         int rc;
-        const int tst = p->tuned_staged[inverse ? 1 : 0];
-        const bool want_staged = want_overlap && (tst >= 0 ? tst != 0 : p->staged != 0) && p->nslots >= 3 && p->blocked_ch > 0 && (!inverse || p->blocked_inv);
-        if (want_staged) { rc = inverse ? build_staged_slab_inverse(p, sc) : build_staged_slab(p, sc); sc.staged = true; }
-        else if (want_overlap) rc = build_overlapped_slab(p, inverse ? 1 : 0, sc);
+        if (want_overlap) rc = build_overlapped_slab(p, inverse ? 1 : 0, sc);
         else if (want_pencil_overlap) rc = build_overlapped_pencil(p, sc);
         else rc = build_schedule(p, inverse ? 1 : 0, d, sc);
         if (rc) return rc;
         if (g_view_error) return fail(DFFT_ERR_STATE, "internal: segments of one view disagree on the axis stride");
-        const int ts = p->tuned_swap[inverse ? 1 : 0];
-        sc.prio_swap = sc.overlapped && !sc.staged && (ts >= 0 ? ts != 0 : p->ovl_prio_swap != 0);
     }
     *out = &sc;
     return DFFT_SUCCESS;
@@ -2392,8 +1898,6 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
     p->any_direct = (p->direct1 && p->grp[1].size() > 1) || (p->direct2 && p->grp[2].size() > 1);
     p->nslots = (d1 ? 1 : 0) + (d2 ? 1 : 0) + ((!d1 || !d2) ? 2 : 0);
     if (p->nslots < 2) p->nslots = 2;
-    // the staged overlapped schedule of the slab (y pass local + pusher) needs a staging slot besides the two hand-over slots
-    if (decomp == DFFT_SLAB_ZY_THEN_X && P > 1 && p->direct2 && p->cfg.send_method == DFFT_SEND_STREAMS && p->nslots < 3) p->nslots = 3;
     size_t dom = 0;
     for (int r = 0; r < P; ++r) dom = std::max(dom, g.domain_elems(r));
     p->domain_bytes = g.domain_elems(me) * p->esize;
@@ -2410,9 +1914,6 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         // NVLink store efficiency grows with the contiguous run per row: 64-byte rows reach 434 GB/s per direction,
         // 128-byte rows 700 GB/s, 2 KB runs 704 GB/s (profiles/r01_8gpu, r01_bench_n2_*): exchanging passes prefer the
         // wide tile even though it is slower as a purely local pass.  DFFT_XCHG_WIDE=0 keeps the narrow tile.
-        if (const char* ps = getenv("DFFT_OVL_PRIO_SWAP")) p->ovl_prio_swap = atoi(ps) != 0;
-        if (const char* sg = getenv("DFFT_STAGED")) p->staged = atoi(sg) != 0;
-        if (const char* pc = getenv("DFFT_PUSH_CTAS")) p->push_ctas = std::max(1, std::min(1024, atoi(pc)));
         if (const char* eg = getenv("DFFT_OVL_GROUPS")) p->ovl_groups = std::max(1, std::min(16, atoi(eg)));
         if (const char* ec = getenv("DFFT_OVL_CHUNKS")) p->ovl_chunks = std::max(1, std::min(16, atoi(ec)));
         const char* et = getenv("DFFT_RENDEZVOUS_TIMEOUT_S");
@@ -2463,12 +1964,9 @@ int dfft_plan_create(dfft_comm_t comm, const dfft_config* config, int decomp, in
         cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
         if (cudaStreamCreateWithPriority(&p->aux[0], cudaStreamNonBlocking, hi) != cudaSuccess ||
             cudaStreamCreateWithPriority(&p->aux[1], cudaStreamNonBlocking, lo) != cudaSuccess ||
-            cudaStreamCreateWithPriority(&p->aux[2], cudaStreamNonBlocking, lo) != cudaSuccess ||
-            cudaStreamCreateWithPriority(&p->aux[3], cudaStreamNonBlocking, hi) != cudaSuccess ||
             cudaEventCreateWithFlags(&p->fork_ev, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&p->join_ev[0], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&p->join_ev[1], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&p->join_ev[2], cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&p->join_ev[1], cudaEventDisableTiming) != cudaSuccess) {
             delete p;
             return fail(DFFT_ERR_CUDA, "stream / event creation failed");
         }
@@ -2521,10 +2019,10 @@ int dfft_plan_destroy(dfft_plan_t p) {
     for (cudaEvent_t e : p->tl_events) cudaEventDestroy(e);
     for (cudaEvent_t e : p->sync_events) cudaEventDestroy(e);
     if (p->fork_ev) cudaEventDestroy(p->fork_ev);
-    for (int a = 0; a < 3; ++a)
+    for (int a = 0; a < 2; ++a) {
         if (p->join_ev[a]) cudaEventDestroy(p->join_ev[a]);
-    for (int a = 0; a < 4; ++a)
         if (p->aux[a]) cudaStreamDestroy(p->aux[a]);
+    }
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     if (p->entry_ev) cudaEventDestroy(p->entry_ev);
     delete p;
@@ -2681,11 +2179,9 @@ int dfft_get_step_times(dfft_plan_t p, double* ms, int capacity) {
 // caller's buffers with each candidate — the sequential schedule and overlapped schedules with different numbers of
 // CTAs for the exchanging pass — and keeps the fastest one, judged by the slowest rank.  Collective; `out` is
 // overwritten; the input is left intact.  Only plans created with send_method Streams have alternatives.
-static std::string cand_name(int seq, int ctas, int swap, int staged, int groups) {
+static std::string cand_name(int seq, int ctas, int groups, int chunks) {
     if (seq) return "sequential";
-    if (staged) return "overlapped/staged (local pass + " + std::to_string(ctas) + "-CTA pusher)";
-    return "overlapped/" + (ctas > 0 ? std::to_string(ctas) + " CTAs" : std::string("full grid")) + (swap ? "/local passes first" : "") +
-           (groups == 1 ? "/z pass unsplit" : "");
+    return "overlapped/" + std::to_string(ctas) + " CTAs/" + std::to_string(groups) + " groups/" + std::to_string(chunks) + " chunks";
 }
 int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int reps) {
     if (!p) return fail(DFFT_ERR_INVALID, "null plan");
@@ -2696,26 +2192,26 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
     if (reps < 1) reps = 3;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->comm->device);
-    struct Cand { int seq; int ctas; int swap; int staged; int groups; };  // groups: plane groups of the z pass (0 = the plan's default)
+    // candidates: the sequential schedule, and overlapped schedules over a small grid of (CTAs of the exchanging pass,
+    // plane groups of the z pass, z chunks of the y / x passes).  One candidate costs reps + 1 transforms (milliseconds).
+    struct Cand { int seq; int ctas; int groups; int chunks; };
     std::vector<Cand> cands;
-    cands.push_back({1, 0, 0, 0, 0});
-    const int groups_default = p->ovl_groups;
+    cands.push_back({1, 0, 0, 0});
     const bool streams = p->cfg.send_method == DFFT_SEND_STREAMS || (p->g.decomp == DFFT_PENCIL && p->cfg.send_method2 == DFFT_SEND_STREAMS);
     const bool has_overlap = streams && p->P > 1 && p->xchg_ctas >= 0 &&
                              ((p->g.decomp == DFFT_SLAB_ZY_THEN_X && p->direct2) ||
                               (p->g.decomp == DFFT_PENCIL && !inverse && p->direct1 && p->direct2 && p->grp[1].size() > 1 && p->grp[2].size() > 1 &&
                                pencil_overlap_enabled()));
+    const int groups_default = p->ovl_groups, chunks_default = p->ovl_chunks;
     if (has_overlap) {
-        // exchange pass as a capped persistent grid that outranks the local passes ...
-        for (int c : {sms / 3, (2 * sms) / 3, sms, 2 * sms}) cands.push_back({0, c, 0, 0, 0});
-        // ... the same without splitting the z pass into plane groups (z alone at full speed, then y chunks | x chunks)
-        if (!inverse)
-            for (int c : {sms / 3, (2 * sms) / 3}) cands.push_back({0, c, 0, 0, 1});
-        // ... or at full size but outranked by them (the local passes take every CTA slot that frees up)
-        for (int c : {0, sms}) cands.push_back({0, c, 1, 0, 0});
-        // ... or as a local pass whose output a small copy kernel pushes to the peers (slab forward)
-        if (p->g.decomp == DFFT_SLAB_ZY_THEN_X && p->nslots >= 3 && p->blocked_ch > 0 && (!inverse || p->blocked_inv))
-            for (int c : {64, 128}) cands.push_back({0, c, 0, 1, 0});  // ctas = CTAs of the pusher
+        const int cta_list[] = {sms / 3, sms / 2, (2 * sms) / 3, (5 * sms) / 6, sms, 2 * sms};
+        for (int c : cta_list) {
+            for (int ch : {4, 8}) {
+                if (inverse) cands.push_back({0, c, 1, ch});  // the inverse has no plane groups (the exchanging x pass comes first)
+                else
+                    for (int g_ : {1, 4}) cands.push_back({0, c, g_, ch});
+            }
+        }
     }
     p->tune_report.clear();
     if (cands.size() == 1) {
@@ -2727,20 +2223,21 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
     CK_CUDA(cudaEventCreate(&e1));
     const bool was_timing = p->timing;
     p->timing = false;
+    auto apply = [&](const Cand& c) {
+        p->tuned_seq[dir] = c.seq;
+        p->tuned_ctas[dir] = c.seq ? -2 : c.ctas;
+        p->tuned_chunks[dir] = c.seq ? 0 : c.chunks;
+        if (!inverse) p->ovl_groups = (!c.seq && c.groups > 0) ? c.groups : groups_default;
+        p->sched[dir][2] = Schedule();
+    };
     int best = 0;
     double best_ms = 1e30;
     std::string rep;
     for (size_t k = 0; k < cands.size(); ++k) {
-        p->tuned_seq[dir] = cands[k].seq;
-        p->tuned_ctas[dir] = cands[k].seq ? -2 : cands[k].ctas;
-        p->tuned_swap[dir] = cands[k].swap;
-        p->tuned_staged[dir] = cands[k].staged;
-        p->tuned_push[dir] = cands[k].staged ? cands[k].ctas : 0;
-        if (!inverse) p->ovl_groups = cands[k].groups > 0 ? cands[k].groups : groups_default;
-        p->sched[dir][2] = Schedule();
+        apply(cands[k]);
         Schedule* sc = nullptr;
         int rc = get_schedule(p, inverse, 3, &sc);
-        if (rc) return rc;
+        if (rc) continue;  // a candidate this geometry cannot build: skip it (every rank takes the same branch)
         for (int it = 0; it < reps + 1; ++it) {
             if (it == 1) CK_CUDA(cudaEventRecord(e0, p->own_stream));
             rc = run_schedule(p, *sc, out, in, p->own_stream);
@@ -2757,20 +2254,16 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
         if (rc) return rc;
         double worst = 0;
         for (int r = 0; r < p->P; ++r) worst = std::max(worst, reinterpret_cast<const double*>(all.data())[r]);
-        rep += (k ? ", " : "") + cand_name(cands[k].seq, cands[k].ctas, cands[k].swap, cands[k].staged, cands[k].groups) + " " + std::to_string(worst).substr(0, 6) + " ms";
+        rep += (k ? ", " : "") + cand_name(cands[k].seq, cands[k].ctas, cands[k].groups, cands[k].chunks) + " " + std::to_string(worst).substr(0, 6) + " ms";
         if (worst < best_ms) { best_ms = worst; best = int(k); }
     }
-    p->tuned_seq[dir] = cands[best].seq;
-    p->tuned_ctas[dir] = cands[best].seq ? -2 : cands[best].ctas;
-    p->tuned_swap[dir] = cands[best].swap;
-    p->tuned_staged[dir] = cands[best].staged;
-    p->tuned_push[dir] = cands[best].staged ? cands[best].ctas : 0;
-    if (!inverse) p->ovl_groups = cands[best].groups > 0 ? cands[best].groups : groups_default;
-    p->sched[dir][2] = Schedule();
+    apply(cands[best]);
+    (void)chunks_default;
     p->timing = was_timing;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    p->tune_report = std::string(inverse ? "inverse: " : "forward: ") + rep + " -> " + cand_name(cands[best].seq, cands[best].ctas, cands[best].swap, cands[best].staged, cands[best].groups);
+    p->tune_report = std::string(inverse ? "inverse: " : "forward: ") + rep + " -> " +
+                     cand_name(cands[best].seq, cands[best].ctas, cands[best].groups, cands[best].chunks);
     return best;
 }
 const char* dfft_plan_tune_report(dfft_plan_t p) { return p ? p->tune_report.c_str() : nullptr; }
@@ -2843,16 +2336,6 @@ int dfft_plan_describe(dfft_plan_t p, int inverse, int d, char* buf, size_t capa
             json_view(o, s_.prm.in, p->tabs);
             o += ",\"out\":";
             json_view(o, s_.prm.out, p->tabs);
-        } else if (s_.type == STEP_PUSH) {
-            o += ",\"descs\":[";
-            for (size_t i = 0; i < s_.push.size(); ++i) {
-                const PushDesc& d_ = s_.push[i];
-                if (i) o += ",";
-                o += "{\"src\":" + std::to_string((unsigned long long)d_.src) + ",\"dst\":" + std::to_string((unsigned long long)d_.dst) + ",\"row_bytes\":" +
-                     std::to_string(d_.row_bytes) + ",\"src_pitch\":" + std::to_string(d_.src_pitch) + ",\"dst_pitch\":" + std::to_string(d_.dst_pitch) +
-                     ",\"rows\":" + std::to_string(d_.rows) + "}";
-            }
-            o += "]";
         } else if (s_.type == STEP_RENDEZVOUS) {
             o += ",\"group\":" + std::to_string(s_.group);
         } else {

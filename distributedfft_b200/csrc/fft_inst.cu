@@ -123,19 +123,6 @@ static cudaError_t launch_tiled(const FftParams& p_in, cudaStream_t stream, long
             return cudaGetLastError();
         }
     }
-    {
-        // TMA bulk-store variant (see fft_c2c_bulk_kernel): only when the launcher's contract holds
-        if (p.bulk_out && p.in.nseg == 1 && p.out.sN == TB && p.B == TB && (TB * sizeof(cx<T>)) % 16 == 0) {
-            auto bf = fft_c2c_bulk_kernel<T, LOG2N, LOG2E, TB, false>;
-            auto bi = fft_c2c_bulk_kernel<T, LOG2N, LOG2E, TB, true>;
-            static cudaError_t onceb = set_smem(bf, C::SMEM_BYTES) != cudaSuccess ? cudaErrorInvalidValue : set_smem(bi, C::SMEM_BYTES);
-            if (onceb != cudaSuccess) return onceb;
-            const unsigned gb = unsigned((p.max_ctas > 0 && grid > p.max_ctas) ? p.max_ctas : grid);
-            if (p.inverse) bi<<<gb, C::THREADS, C::SMEM_BYTES, stream>>>(p);
-            else bf<<<gb, C::THREADS, C::SMEM_BYTES, stream>>>(p);
-            return cudaGetLastError();
-        }
-    }
     unsigned g = unsigned((p.max_ctas > 0 && grid > p.max_ctas) ? p.max_ctas : grid);
     const int cl = env_int("DFFT_CLUSTER", 0);
     if (cl > 1 && cl <= 8) {

@@ -59,7 +59,8 @@ struct FftParams {
     int max_ctas;     // > 0: run as a persistent kernel on at most this many CTAs (SM partitioning for the
                       // overlapped schedule: the exchange pass keeps a few SMs, the local passes the rest)
     int tile_pref;    // TILED: 0 automatic, 1 narrow tiles, 2 wide tiles
-    int bulk_out;     // TILED, experimental: store each destination's rows with one cp.async.bulk (TMA) from shared memory
+    int bulk_out;     // TILED, TMA-fed kernel, experiment (DFFT_BULK_STORE=1): store each destination's rows with one
+                      // cp.async.bulk from shared memory instead of 16-byte stores from registers
     int tile_swz;     // TILED: log2 G of the tile-order blocking: G x G tiles of (a0, a1) are numbered consecutively, so
                       // that CTAs running at the same time touch neighbouring rows on BOTH sides of a transposing pass
                       // (0 = plain order: b tiles fastest, then a1, then a0)
@@ -382,83 +383,6 @@ fft_c2c_kernel(const __grid_constant__ FftParams p) {
         }
     }
 }
-
-// ---- C2C TILED pass with TMA bulk stores (EXPERIMENTAL, DFFT_BULK_STORE=1) --------------------------------
-// For the exchanging y pass with the blocked hand-over layout the rows a tile sends to one destination are
-// adjacent in the receiver's slot ([Nzc/CH][Nx][Ny_q][CH], tile width = CH).  Instead of 16-byte stores from
-// registers, the finished tile is written once more to shared memory in natural [n][TB] order and ONE
-// cp.async.bulk.global.shared::cta per destination moves Ny_q * CH * sizeof(complex) contiguous bytes (16 KB for the
-// 1024-point pass on 8 GPUs) into the peer's buffer: the TMA engine emits maximum-size NVLink packets and the SM
-// issues no store instructions.  Requirements (checked by the launcher): out.sN == TB == B, unpadded tile rows,
-// single-segment input.  Not timed on hardware yet.
-template <typename T, int LOG2N, int LOG2E, int TB, bool INV>
-__global__ void __launch_bounds__((1 << (LOG2N - LOG2E)) * TB, min_ctas_per_sm<T, LOG2E>((1 << (LOG2N - LOG2E)) * TB))
-fft_c2c_bulk_kernel(const __grid_constant__ FftParams p) {
-    using C = CtaFft<T, LOG2N, LOG2E, TB, true>;
-    using LA = LineAccess<T, 1>;
-    using TC = TileCoord<C, true, TB>;
-    constexpr int E = C::E, TPL = C::TPL, N = C::N;
-    // the staging copy of the finished tile is written UNPADDED ([n][TB], N*TB elements <= the padded tile) once the
-    // last gather has left the buffer, so narrow (padded) tiles qualify as well
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
-    unsigned long long* tab_in = reinterpret_cast<unsigned long long*>(smem_raw + C::TILE_BYTES);
-    unsigned long long* tab_out = tab_in + MAXSEG;
-    const long long ntiles = TC::num_tiles(p);
-
-#pragma unroll 1
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const TC tc(p, tile);
-        const int j = tc.j, t = tc.t;
-        // table of destination row-0 addresses (tile column 0), one per segment
-        for (int s = threadIdx.x; s < p.out.nseg; s += C::THREADS) {
-            const Seg& g = p.out.seg[s];
-            cx<T>* q = reinterpret_cast<cx<T>*>(g.base) + (tc.a0 * g.sA0 + tc.a1 * g.sA1 - (long long)g.n0 * p.out.sN);
-            tab_out[s] = reinterpret_cast<unsigned long long>(q);
-        }
-        const LA in(p.in, tab_in, 0, tc.a0, tc.a1, tc.b);
-        cx<T> v[E];
-        {
-            const long long step = (long long)TPL * p.in.sN;
-            const cx<T>* q = in.p0 + (long long)j * p.in.sN;
-#pragma unroll
-            for (int e = 0; e < E; ++e) { v[e] = ld_elem<T>(q); q += step; }
-            if constexpr (INV) {
-#pragma unroll
-                for (int e = 0; e < E; ++e) v[e] = cswap(v[e]);
-            }
-        }
-        C::template stages<0>(v, j, t, sm, reinterpret_cast<const cx<T>*>(p.tw));
-        // finished tile -> shared memory in natural order [n][TB]
-        if constexpr (C::NST > 1) __syncthreads();
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const cx<T> x = v[C::Core::final_slot(e)];
-            sm[(j + e * TPL) * TB + t] = INV ? cswap(x) : x;
-        }
-        // make the generic-proxy writes visible to the async proxy, then one bulk store per destination
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (int(threadIdx.x) < p.out.nseg) {
-            const int s = threadIdx.x;
-            const int n0 = p.out.nseg > 1 ? p.out.seg[s].n0 : 0;
-            const int n1 = (s + 1 < p.out.nseg) ? p.out.seg[s + 1].n0 : N;
-            const unsigned bytes = unsigned(n1 - n0) * TB * unsigned(sizeof(cx<T>));
-            const unsigned src = unsigned(__cvta_generic_to_shared(sm + n0 * TB));
-            const unsigned long long dst = tab_out[s] + (unsigned long long)n0 * TB * sizeof(cx<T>);
-            if (bytes) {
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may be reused
-            }
-        }
-        __syncthreads();
-    }
-    // all bulk stores of this CTA have been written (not only read from shared memory) before the kernel ends:
-    // the rendezvous that follows publishes them to the peers
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-
 
 // ---- C2C TILED pass fed by TMA ----------------------------------------------------------------------------
 // Same tile, same stages, but the N x TB input tile is fetched by the TMA engine (cp.async.bulk.tensor, SASS UTMALDG)

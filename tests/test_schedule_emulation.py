@@ -134,22 +134,6 @@ def run_case(P, decomp, transform, shape, p1, p2, comm_method, send_method, inve
             if st["type"] == 1:
                 last_rdv[r] = k
                 continue
-            if st["type"] == 3:  # pusher: strided byte copies from a local staging slot into the peers' slots
-                for dsc in st["descs"]:
-                    own_src = owner_of(dsc["src"])
-                    assert own_src is not None and own_src[0] == r, "the pusher reads local memory only"
-                    own_dst = owner_of(dsc["dst"])
-                    assert own_dst is not None
-                    if own_dst[0] != r:  # (a descriptor may also move a staged block into the rank's own slot)
-                        assert last_rdv[r] >= 0, f"rank {r} pushes into rank {own_dst[0]}'s slot before its entry rendezvous"
-                        last_remote_write[own_dst] = k
-                    assert dsc["row_bytes"] % 16 == 0 and dsc["src_pitch"] % 16 == 0 and dsc["dst_pitch"] % 16 == 0
-                    n16 = dsc["row_bytes"] // 16
-                    for row in range(dsc["rows"]):
-                        src, so = mem.resolve(dsc["src"] + row * dsc["src_pitch"])
-                        dst, do = mem.resolve(dsc["dst"] + row * dsc["dst_pitch"])
-                        pending.append((dst, do, src[so:so + n16].copy()))
-                continue
             if st["type"] == 2:  # all-to-all-v between staging slots
                 sb = scheds[r]["slots"][st["send_slot"]][r]
                 for peer in st["peers"]:
@@ -283,20 +267,17 @@ def test_layout_knobs(env, inverse, monkeypatch):
     assert run_case(4, PE, dfft.R2C, (8, 16, 512), 2, 2, P2P, SYNC, inverse, 3) < 1e-12
 
 
-@pytest.mark.parametrize("P,transform,shape", [(8, dfft.C2C, (32, 16, 256)), (2, dfft.C2C, (8, 8, 128)), (8, dfft.R2C, (16, 8, 512)), (3, dfft.R2C, (16, 16, 256)),
-                                               (4, dfft.C2C, (128, 128, 128)), (4, dfft.R2C, (64, 32, 1024))])
-def test_staged_slab_schedule(P, transform, shape, monkeypatch):
-    """overlapped slab schedules with a local exchanging pass and the pusher (DFFT_STAGED=1, SendMethod Streams), forward
-    (y pass -> staging -> push) and inverse (x pass -> staging -> push)"""
-    monkeypatch.setenv("DFFT_STAGED", "1")
-    assert run_case(P, SL, transform, shape, P, 1, P2P, STREAMS, 0, 3) < 1e-12
-    sched = describe(0, P, SL, transform, shape, P, 1, P2P, STREAMS, 0, 3)
-    assert sched["overlapped"] and any(s["type"] == 3 for s in sched["steps"]) and sched["nslots"] == 3
-    assert {s["stream"] for s in sched["steps"]} == {0, 1, 2, 3}
-    assert run_case(P, SL, transform, shape, P, 1, P2P, STREAMS, 1, 3) < 1e-12
-    assert any(s["type"] == 3 for s in describe(0, P, SL, transform, shape, P, 1, P2P, STREAMS, 1, 3)["steps"])
-    monkeypatch.delenv("DFFT_STAGED")
-    assert not any(s["type"] == 3 for s in describe(0, P, SL, transform, shape, P, 1, P2P, STREAMS, 0, 3)["steps"])
+@pytest.mark.parametrize("env", [{"DFFT_OVL_GROUPS": "1", "DFFT_OVL_CHUNKS": "8"}, {"DFFT_OVL_GROUPS": "2", "DFFT_OVL_CHUNKS": "2"}, {"DFFT_XCHG_CTAS": "0"}])
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_overlap_granularity_knobs(env, inverse, monkeypatch):
+    """plane groups / z chunks / exchange CTAs of the overlapped schedules (the grid dfft_plan_tune searches)"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    assert run_case(8, SL, dfft.C2C, (32, 16, 512), 8, 1, P2P, STREAMS, inverse, 3) < 1e-12
+    assert run_case(4, SL, dfft.R2C, (16, 16, 1024), 4, 1, P2P, STREAMS, inverse, 3) < 1e-12
+    if not inverse:
+        monkeypatch.setenv("DFFT_PENCIL_OVERLAP", "1")
+        assert run_case(8, PE, dfft.C2C, (16, 8, 2048), 2, 4, P2P, STREAMS, 0, 3) < 1e-12
 
 
 @pytest.mark.parametrize("shape,P", [((128, 128, 128), 4), ((64, 256, 256), 2), ((256, 64, 128), 8), ((16, 16, 128), 1)])
