@@ -1744,6 +1744,29 @@ static int timer_gather(dfft_plan_s* p) {
             if (!strcmp(names[i], p->ev_names[k])) dur[i] = f;
     }
     dur[ns - 1] = last;  // "Run complete"
+    if (p->n_events_used == 2 && p->tl_used >= 2) {
+        // overlapped schedule: the steps ran on several streams and only start / end were marked on the caller's.  The
+        // reference's sections are cumulative times, so a section gets the time at which the LAST step of its kind ended
+        // (step timeline, dfft_get_timeline).
+        const bool pencil = p->g.decomp == DFFT_PENCIL;
+        auto section_of = [&](const char* label) -> const char* {
+            if (!strncmp(label, "z pass", 6)) return p->g.decomp == DFFT_SLAB_ZY_THEN_X ? nullptr : "1D FFT Z-Direction";
+            if (!strncmp(label, "y pass", 6)) return pencil ? "1D FFT Y-Direction" : "2D FFT Y-Z-Direction";
+            if (!strncmp(label, "x pass", 6)) return "1D FFT X-Direction";
+            if (!strcmp(label, "rendezvous 1")) return "First Transpose (Finished Receive)";
+            if (!strcmp(label, "rendezvous 2")) return pencil ? "Second Transpose (Finished Receive)" : "Transpose (Finished Receive)";
+            return nullptr;
+        };
+        for (int i = 0; i + 1 < p->tl_used; i += 2) {
+            const char* sec = section_of(p->tl_labels[i]);
+            if (!sec) continue;
+            float f = 0;
+            CK_CUDA(cudaEventSynchronize(p->tl_events[i + 1]));
+            CK_CUDA(cudaEventElapsedTime(&f, p->events[0], p->tl_events[i + 1]));
+            for (int k = 0; k < ns; ++k)
+                if (!strcmp(names[k], sec) && f > dur[k]) dur[k] = f;
+        }
+    }
     std::vector<char> all;
     int rc = nccl_allgather_bytes(p, dur.data(), sizeof(double) * ns, all);
     if (rc) return rc;
@@ -2208,7 +2231,7 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
             for (int ch : {4, 8}) {
                 if (inverse) cands.push_back({0, c, 1, ch});  // the inverse has no plane groups (the exchanging x pass comes first)
                 else
-                    for (int g_ : {1, 4}) cands.push_back({0, c, g_, ch});
+                    for (int g_ : {1, 2, 4}) cands.push_back({0, c, g_, ch});
             }
         }
     }

@@ -292,6 +292,21 @@ def test_timer_csv_schema(tmp_path):
     plan.destroy()
 
 
+def test_plan_tune_single_rank_has_no_alternatives():
+    """dfft_plan_tune on one rank: nothing to choose (no exchange), the plan keeps working"""
+    shape = (64, 32, 128)
+    cfg = dfft.Configurations(send_method=dfft.SendMethod.Streams)
+    plan = dfft.MPIcuFFT_Slab(cfg, dfft.Comm(), precision="double", transform="r2c")
+    plan.initFFT(dfft.GlobalSize(*shape), None, True)
+    x = dev(O.real_input(shape))
+    out = torch.empty((64, 32, 65), dtype=torch.complex128, device="cuda")
+    rep = plan.tune(out, x, dfft.FORWARD, 2)
+    assert "no alternatives" in rep
+    plan.execR2C(out, x)
+    assert O.rel_l2(host(out), O.fft_r2c(host(x))) < 1e-10
+    plan.destroy()
+
+
 def test_step_timeline():
     """dfft_get_timeline: (label, stream, begin, end) of every step of the last timed exec"""
     shape = (64, 64, 64)
