@@ -212,6 +212,41 @@ def work_area_inside_allocation(comm, rank, world):
     return fails
 
 
+def timer_csv_of_overlapped_run(comm, rank, world):
+    """Phase-timer CSV (src/timer.cpp:58-101 schema) of an overlapped (Streams) slab plan: the sections come from the step
+    timeline and must be filled and ordered like the reference's cumulative times."""
+    import tempfile
+    box = [tempfile.mkdtemp(prefix="dfft_csv_") if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    shape = (64, 64, 256)
+    cfg = dfft.Configurations(send_method=dfft.SendMethod.Streams, warmup_rounds=1, benchmark_dir=box[0])
+    plan = dfft.MPIcuFFT_Slab(cfg, comm, precision="double", transform="r2c")
+    plan.initFFT(dfft.GlobalSize(*shape), None, True)
+    isz = plan.getInSize()
+    x = torch.rand(isz, device="cuda", dtype=torch.float64)
+    out = torch.empty(plan.getDomainSize() // 16, dtype=torch.complex128, device="cuda")
+    for _ in range(3):
+        plan.execR2C(out, x)
+    plan.destroy()
+    ok = True
+    if rank == 0:
+        path = os.path.join(box[0], "slab_default", f"test_0_0_1_{shape[0]}_{shape[1]}_{shape[2]}_1_{world}.csv")
+        ok = os.path.exists(path)
+        if ok:
+            blocks = [b for b in open(path).read().split("\n\n") if b.strip()]
+            rows = [r.split(",") for r in blocks[-1].strip().split("\n")]
+            vals = {r[0]: [float(v) for v in r[1:1 + world]] for r in rows if r[0] and r[0] != ""}
+            try:
+                ok = all(0 < a <= b + 1e-3 <= c + 2e-3 for a, b, c in zip(vals["2D FFT Y-Z-Direction"], vals["1D FFT X-Direction"], vals["Run complete"]))
+                ok = ok and all(v > 0 for v in vals["Transpose (Finished Receive)"])
+            except KeyError:
+                ok = False
+        print(f"{'ok  ' if ok else 'FAIL'} timer CSV of an overlapped slab run ({path if ok else box[0]})", flush=True)
+    t = torch.tensor([0.0 if ok else 1.0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
+
+
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -311,6 +346,7 @@ def main():
                   f"{shape} fwd={e[0].item():.2e} inv={e[1].item():.2e}", flush=True)
         fails += int(e[2].item())
         plan.destroy()
+    fails += timer_csv_of_overlapped_run(comm, rank, world)
     if rank == 0:
         print(f"mgpu_parity: {len(cases)} cases, {fails} failed", flush=True)
     dist.destroy_process_group()
