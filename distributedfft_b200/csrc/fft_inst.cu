@@ -57,11 +57,9 @@ static bool make_view_map(const View& v, int A0, int A1, int N, int B, int TB, C
     if ((cuuint64_t(TB) * d0 * 8) % 16) return false;
     cuuint32_t box[4] = {cuuint32_t(TB * d0), cuuint32_t(N < 256 ? N : 256), 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    const int promo = env_int("DFFT_TMA_L2PROMO", 0);
-    const CUtensorMapL2promotion l2 = promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-                                      : (promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : (promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE));
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    // (L2 promotion to 128 / 256 bytes was measured: no effect at 128 bytes, -5 ... -12 % at 256: profiles/r02/axis_f64_s1b_tma_p*.log)
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static int wide_tiles() {
@@ -123,20 +121,7 @@ static cudaError_t launch_tiled(const FftParams& p_in, cudaStream_t stream, long
             return cudaGetLastError();
         }
     }
-    unsigned g = unsigned((p.max_ctas > 0 && grid > p.max_ctas) ? p.max_ctas : grid);
-    const int cl = env_int("DFFT_CLUSTER", 0);
-    if (cl > 1 && cl <= 8) {
-        // experiment: thread-block clusters of `cl` CTAs = tiles that are adjacent along b are co-scheduled (DRAM page
-        // locality of narrow rows); extra CTAs of the rounded-up grid find no tile and exit
-        g = (g + cl - 1) / cl * cl;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(g); cfg.blockDim = dim3(C::THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, p.inverse ? ki : kf, p);
-    }
+    const unsigned g = unsigned((p.max_ctas > 0 && grid > p.max_ctas) ? p.max_ctas : grid);
     if (p.inverse) ki<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
     else kf<<<g, C::THREADS, C::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();

@@ -94,6 +94,31 @@ def test_job_runner_maps_reference_job_files():
     assert "cli.py pencil" in " ".join(cmds[2]) and "-p1 2" in " ".join(cmds[2])
 
 
+def test_repo_job_files_and_pencil_flag_aliases():
+    """tests/jobs/*.json (this repo's validation sweeps in the reference's schema) expand to argv sets that tests/cli.py
+    parses, including the pencil executable's -comm1/-snd1 spelling (tests/src/pencil/main.cpp:173-178)."""
+    import glob
+    import importlib.util
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    spec = importlib.util.spec_from_file_location("launch_jobs", os.path.join(ROOT, "tests", "launch_jobs.py"))
+    lj = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(lj)
+    import cli
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "jobs", "*.json")))
+    assert len(files) >= 4
+    seen = 0
+    for f in files:
+        for cmd in lj.commands(json.load(open(f)), 8, 256):
+            a = cli.parse(cmd[cmd.index(os.path.join(ROOT, "tests", "cli.py")) + 1:])
+            assert a.testcase == 4 and a.double_prec and a.nx in (128, 256)
+            seen += 1
+    assert seen >= 2 * (9 + 40)
+    a = cli.parse("pencil -nx 8 -ny 8 -nz 8 -comm1 All2All -snd1 Streams -comm2 Peer2Peer -snd2 MPI_Type -p1 2 -p2 2".split())
+    assert (a.comm, a.snd, a.comm2, a.snd2) == ("All2All", "Streams", "Peer2Peer", "MPI_Type")
+
+
 def test_bench_reference_arm_runs_on_cpu():
     """bench.py --impl reference (the CPU arm: oracle port, pocketfft on the host cores) prints the contract's JSON
     line and needs no GPU."""

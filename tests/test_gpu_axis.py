@@ -71,9 +71,9 @@ def test_strided_c2c(prec, a, n, b):
 
 
 @pytest.mark.parametrize("env", [{"DFFT_WIDE_TILES": "1"}, {"DFFT_WIDE_TILES": "-1"}, {"DFFT_TMA": "1"}, {"DFFT_TMA": "1", "DFFT_WIDE_TILES": "1"},
-                                 {"DFFT_TMA": "1", "DFFT_TMA_L2PROMO": "2"}, {"DFFT_CLUSTER": "4"}, {"DFFT_TMA": "0"}, {"DFFT_TILE_SWZ": "2"}])
+                                 {"DFFT_TMA": "0"}, {"DFFT_TILE_SWZ": "2"}, {"DFFT_TMA": "1", "DFFT_TILE_SWZ": "1"}])
 def test_kernel_variants(env, monkeypatch):
-    """The alternative kernel variants (wide tiles, TMA-fed persistent kernel, cluster launch) are selected by
+    """The alternative kernel variants (wide tiles, TMA-fed persistent kernel, tile-order blocking) are selected by
     environment variables that the launcher reads at every launch."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
