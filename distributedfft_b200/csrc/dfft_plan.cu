@@ -270,6 +270,7 @@ struct dfft_plan_s {
     int xchg_ctas = 0;                            // SMs given to the exchange pass in overlapped schedules
     int tuned_seq[2] = {0, 0};                    // dfft_plan_tune: [fwd/inv] 1 = the sequential schedule won
     int tuned_chunks[2] = {0, 0};                 // dfft_plan_tune: [fwd/inv] z chunks of the winning overlapped schedule (0 = ovl_chunks)
+    int tuned_groups_inv = 0;                     // dfft_plan_tune: plane groups of the inverse overlapped pencil schedule (0 = ovl_groups)
     int tuned_ctas[2] = {-2, -2};                 // dfft_plan_tune: [fwd/inv] exchange CTAs of the winning overlapped schedule (-2 = not tuned)
     std::string tune_report;
     int ovl_groups = 4, ovl_chunks = 4;           // overlapped schedules: plane groups of the z pass, z chunks of the y / x passes
@@ -330,7 +331,7 @@ namespace dfft {
 
 static int build_schedule(dfft_plan_s* p, int inverse, int d, Schedule& sc);
 static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc);
-static int build_overlapped_pencil(dfft_plan_s* p, Schedule& sc);
+static int build_overlapped_pencil(dfft_plan_s* p, int inverse, Schedule& sc);
 static bool pencil_overlap_enabled();
 
 }  // namespace dfft
@@ -1187,19 +1188,193 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
 
 namespace dfft {
 
-static bool pencil_overlap_enabled() {
-    const char* e = getenv("DFFT_PENCIL_OVERLAP");  // default on; DFFT_PENCIL_OVERLAP=0 keeps Streams plans sequential
-    return !e || atoi(e) != 0;
+// DFFT_PENCIL_OVERLAP: 1 (default) = Streams plans on a grid with two real transpositions run the forward overlapped
+// schedule, and dfft_plan_tune may select an overlapped schedule for any grid and direction after measuring it;
+// 0 = sequential schedules only; 2 = overlapped schedules wherever they can be built, untuned (tests, experiments).
+static int pencil_overlap_mode() {
+    const char* e = getenv("DFFT_PENCIL_OVERLAP");
+    return e ? atoi(e) : 1;
+}
+static bool pencil_overlap_enabled() { return pencil_overlap_mode() != 0; }
+
+// inverse half of build_overlapped_pencil (see the comment there); NG plane groups, the same on every rank
+static int build_overlapped_pencil_inverse(dfft_plan_s* p, Schedule& sc, size_t NG) {
+    const Geometry& g = p->g;
+    const int me = p->rank;
+    const int pi = g.pi(me), pj = g.pj(me);
+    const size_t es = p->esize;
+    const bool c2c = g.transform == DFFT_C2C;
+    Tables& T = p->tabs;
+    const size_t ny = g.ny, nx = g.nx, nzc = g.nzc;
+    const size_t nx_i = g.sx.size[pi];
+    const size_t ny_j = g.sy.size[pj];
+    const size_t nz_j = g.sz.size[pj], z0_j = g.sz.start[pj];
+    const size_t oy_i = g.oy.size[pi], oy0_i = g.oy.start[pi];
+    const std::vector<int>& G1 = p->grp[1];
+    const std::vector<int>& G2 = p->grp[2];
+    const int D1 = 0, D2 = 1;
+    auto slotp = [&](int s_, int r) -> void* { return p->slot_ptr[s_][r]; };
+    int nev = 0;
+    auto new_pass = [&](PassKind kind, size_t n, const char* label, Step& s) -> int {
+        s = Step();
+        s.type = STEP_PASS;
+        s.kind = kind;
+        s.label = label;
+        s.log2n = ilog2_exact(n);
+        if (s.log2n < 1 || s.log2n > MAX_LOG2N) return fail(DFFT_ERR_UNSUPPORTED, "unsupported axis length");
+        s.prm.A0 = 1; s.prm.A1 = 1; s.prm.B = 1;
+        s.prm.inverse = 1;
+        void* tw = nullptr;
+        if (T.get_tw(s.log2n, &tw) != cudaSuccess) return fail(DFFT_ERR_CUDA, "twiddle table allocation failed");
+        s.prm.tw = tw;
+        if (kind == PASS_C2R) {
+            void* tw2 = nullptr;
+            if (T.get_tw2(s.log2n, &tw2) != cudaSuccess) return fail(DFFT_ERR_CUDA, "twiddle table allocation failed");
+            s.prm.tw2 = tw2;
+        }
+        return DFFT_SUCCESS;
+    };
+    auto rendezvous = [&](int group, int stream) {
+        Step s;
+        s.type = STEP_RENDEZVOUS;
+        s.label = group == 0 ? "entry rendezvous" : (group == 1 ? "rendezvous 1" : "rendezvous 2");
+        s.group = group;
+        s.phase_id = group;
+        s.stream = stream;
+        return s;
+    };
+    Split groups;
+    groups.make(nx_i, NG);
+    // hand-over of the x -> y transposition: blocked [nz_j/CH][ny][nx_q][CH] + plain tail [nx_q][ny][rem] (build_schedule)
+    const size_t CH = p->blocked_inv ? size_t(p->blocked_ch) : 0;
+    const size_t rem = CH ? nz_j % CH : 0, nzm = nz_j - rem;
+    bool any_rem = false;  // ranks without leftover columns run the tail steps as empty passes: same step list everywhere
+    if (CH) for (size_t v : g.sz.size) any_rem = any_rem || (v % CH != 0);
+    const unsigned char *tab_x = nullptr, *tab_y_in = nullptr;
+    if (T.seg_table(g.sx, &tab_x) != cudaSuccess || T.seg_table(g.sy, &tab_y_in) != cudaSuccess) return fail(DFFT_ERR_CUDA, "segment table");
+    int rc;
+
+    sc.steps.push_back(rendezvous(0, 0));  // everyone has left the previous exec
+    // x pass on the caller's [nx][oy_i][nz_j], whole, uncapped: nothing local can run beside it yet
+    {
+        Step s;
+        rc = new_pass(PASS_C2C_TILED, nx, "x pass", s);
+        if (rc) return rc;
+        s.in_user = 1;
+        s.prm.tile_pref = G2.size() > 1 ? p->xchg_tile_pref : 1;
+        if (CH) {
+            s.prm.A0 = int(oy_i); s.prm.A1 = int(nzm / CH); s.prm.B = int(CH);
+            s.prm.in = single_view(nullptr, (long long)nz_j, (long long)CH, (long long)(oy_i * nz_j));
+            s.prm.bulk_out = G2.size() > 1 ? p->bulk_store : 0;
+            seg_view(s.prm.out, tab_x, G2, [&](int q, int r) {
+                const size_t nxq = g.sx.size[q];
+                return mkseg(eptr(slotp(D2, r), oy0_i * nxq * CH, es), (long long)(nxq * CH), (long long)(ny * nxq * CH), (long long)CH, g.sx.start[q]);
+            });
+            sc.steps.push_back(s);
+            if (any_rem) {
+                Step t = s;
+                t.label = "x pass (tail)";
+                t.prm.bulk_out = 0;
+                t.prm.A0 = int(oy_i); t.prm.A1 = 1; t.prm.B = int(rem);
+                t.prm.in = single_view((void*)(size_t)(nzm * es), (long long)nz_j, 0, (long long)(oy_i * nz_j));
+                seg_view(t.prm.out, tab_x, G2, [&](int q, int r) {
+                    const size_t nxq = g.sx.size[q];
+                    return mkseg(eptr(slotp(D2, r), ny * nxq * nzm + oy0_i * rem, es), (long long)rem, 0, (long long)(ny * rem), g.sx.start[q]);
+                });
+                sc.steps.push_back(t);
+            }
+        } else {
+            s.prm.A0 = 1; s.prm.A1 = 1; s.prm.B = int(oy_i * nz_j);
+            s.prm.in = single_view(nullptr, 0, 0, (long long)(oy_i * nz_j));
+            // dest (q, j) holds [nx_q][ny][nz_j]; my rows y in [oy0_i, +oy_i)
+            seg_view(s.prm.out, tab_x, G2, [&](int q, int r) {
+                return mkseg(eptr(slotp(D2, r), oy0_i * nz_j, es), 0, 0, (long long)(ny * nz_j), g.sx.start[q]);
+            });
+            sc.steps.push_back(s);
+        }
+    }
+    sc.steps.push_back(rendezvous(2, 0));  // all column peers have delivered their rows
+    const int ev_x = nev++;
+    sc.steps.back().record = ev_x;
+    std::vector<int> ev_y(NG);
+    for (size_t gi = 0; gi < NG; ++gi) {
+        const size_t pl0 = groups.start[gi], npl = groups.size[gi];
+        Step s;
+        rc = new_pass(PASS_C2C_TILED, ny, "y pass", s);
+        if (rc) return rc;
+        s.stream = 1;
+        if (gi == 0) s.waits.push_back(ev_x);
+        s.prm.max_ctas = exchange_ctas(p, 1);
+        s.prm.tile_pref = G1.size() > 1 ? p->xchg_tile_pref : 1;
+        if (CH) {
+            // in = my slot, blocked [nz_j/CH][ny][nx_i][CH]; tile = (x_loc, z block); dest (i, q) holds [nx_i][ny_q][nzc]
+            s.prm.A0 = int(npl); s.prm.A1 = int(nzm / CH); s.prm.B = int(CH);
+            s.prm.in = single_view(eptr(slotp(D2, me), pl0 * CH, es), (long long)CH, (long long)(ny * nx_i * CH), (long long)(nx_i * CH));
+            seg_view(s.prm.out, tab_y_in, G1, [&](int q, int r) {
+                const size_t nyq = g.sy.size[q];
+                return mkseg(eptr(slotp(D1, r), pl0 * nyq * nzc + z0_j, es), (long long)(nyq * nzc), (long long)CH, (long long)nzc, g.sy.start[q]);
+            });
+            if (!any_rem) s.record = ev_y[gi] = nev++;
+            sc.steps.push_back(s);
+            if (any_rem) {
+                Step t = s;
+                t.label = "y pass (tail)";
+                t.waits.clear();
+                t.prm.A0 = int(npl); t.prm.A1 = 1; t.prm.B = int(rem);
+                t.prm.in = single_view(eptr(slotp(D2, me), ny * nx_i * nzm + pl0 * ny * rem, es), (long long)(ny * rem), 0, (long long)rem);
+                seg_view(t.prm.out, tab_y_in, G1, [&](int q, int r) {
+                    const size_t nyq = g.sy.size[q];
+                    return mkseg(eptr(slotp(D1, r), pl0 * nyq * nzc + z0_j + nzm, es), (long long)(nyq * nzc), 0, (long long)nzc, g.sy.start[q]);
+                });
+                t.record = ev_y[gi] = nev++;
+                sc.steps.push_back(t);
+            }
+        } else {
+            s.prm.A0 = int(npl); s.prm.A1 = 1; s.prm.B = int(nz_j);
+            s.prm.in = single_view(eptr(slotp(D2, me), pl0 * ny * nz_j, es), (long long)(ny * nz_j), 0, (long long)nz_j);
+            seg_view(s.prm.out, tab_y_in, G1, [&](int q, int r) {
+                const size_t nyq = g.sy.size[q];
+                return mkseg(eptr(slotp(D1, r), pl0 * nyq * nzc + z0_j, es), (long long)(nyq * nzc), 0, (long long)nzc, g.sy.start[q]);
+            });
+            s.record = ev_y[gi] = nev++;
+            sc.steps.push_back(s);
+        }
+    }
+    const PassKind zkind = c2c ? PASS_C2C_CONTIG : PASS_C2R;
+    const long long zpitch = c2c ? (long long)g.nz : (long long)(g.nz / 2);  // output line pitch in complex units
+    for (size_t gi = 0; gi < NG; ++gi) {
+        const size_t pl0 = groups.start[gi], npl = groups.size[gi];
+        Step r = rendezvous(1, 2);  // all row peers have delivered plane group gi
+        r.waits.push_back(ev_y[gi]);
+        sc.steps.push_back(r);
+        Step s;
+        rc = new_pass(zkind, c2c ? g.nz : g.nz / 2, c2c ? "z pass" : "z pass (C2R)", s);
+        if (rc) return rc;
+        s.prm.A0 = int(npl); s.prm.A1 = int(ny_j);
+        s.prm.in = single_view(eptr(slotp(D1, me), pl0 * ny_j * nzc, es), (long long)(ny_j * nzc), (long long)nzc, 1);
+        s.prm.out = single_view((void*)(size_t)(pl0 * ny_j * size_t(zpitch) * es), zpitch * (long long)ny_j, zpitch, 1);
+        s.out_user = 2;
+        s.stream = 2;
+        sc.steps.push_back(s);
+    }
+    sc.nevents = nev;
+    sc.built = true;
+    return DFFT_SUCCESS;
 }
 
-// Overlapped pencil schedule, forward, Peer2Peer on both transpositions (send_method Streams; measured at 8 GPUs:
-// 2048x2048x1024 complex-float 9.79 ms vs 10.72 ms sequential, profiles/r02/8gpu; parity at full size against cuFFT).
+// Overlapped pencil schedules, Peer2Peer on both transpositions (send_method Streams; forward measured at 8 GPUs:
+// 2048x2048x1024 complex-float 8.67 ms on a 4x2 grid vs 10.7 ms sequential, profiles/r02/8gpu_b; parity at full size
+// against cuFFT).  Forward:
 //   stream 0: z pass per plane group, scattering along z into the row peers' slot A            (NVLink-bound)
 //   stream 1: per plane group: meet the row peers; then the y pass per (plane group, z chunk), persistent on
 //             `xchg_ctas` CTAs, scattering along y into the column peers' slot B                 (NVLink-bound)
 //   stream 2: per z chunk: meet the column peers, x pass of that chunk                           (HBM-bound)
-// Only the x pass can hide behind an exchange (both scatters share the NVLink ports).
-static int build_overlapped_pencil(dfft_plan_s* p, Schedule& sc) {
+// Only the x pass can hide behind an exchange (both scatters share the NVLink ports).  The inverse mirrors it — again
+// only the local pass, now the z pass, can hide:
+//   stream 0: x pass, scattering along x into the column peers' slot B; meet the column peers   (NVLink-bound)
+//   stream 1: y pass per plane group on a capped grid, scattering along y into the row peers' slot A  (NVLink-bound)
+//   stream 2: per plane group: meet the row peers, z pass of that group into the caller's buffer  (HBM-bound)
+static int build_overlapped_pencil(dfft_plan_s* p, int inverse, Schedule& sc) {
     const Geometry& g = p->g;
     const int me = p->rank;
     const int pi = g.pi(me), pj = g.pj(me);
@@ -1227,11 +1402,11 @@ static int build_overlapped_pencil(dfft_plan_s* p, Schedule& sc) {
         s.log2n = ilog2_exact(n);
         if (s.log2n < 1 || s.log2n > MAX_LOG2N) return fail(DFFT_ERR_UNSUPPORTED, "unsupported axis length");
         s.prm.A0 = 1; s.prm.A1 = 1; s.prm.B = 1;
-        s.prm.inverse = 0;
+        s.prm.inverse = inverse;
         void* tw = nullptr;
         if (T.get_tw(s.log2n, &tw) != cudaSuccess) return fail(DFFT_ERR_CUDA, "twiddle table allocation failed");
         s.prm.tw = tw;
-        if (kind == PASS_R2C) {
+        if (kind == PASS_R2C || kind == PASS_C2R) {
             void* tw2 = nullptr;
             if (T.get_tw2(s.log2n, &tw2) != cudaSuccess) return fail(DFFT_ERR_CUDA, "twiddle table allocation failed");
             s.prm.tw2 = tw2;
@@ -1252,7 +1427,8 @@ static int build_overlapped_pencil(dfft_plan_s* p, Schedule& sc) {
     size_t min_nx = nx, min_nz = g.nzc;
     for (size_t v : g.sx.size) min_nx = std::min(min_nx, v);
     for (size_t v : g.sz.size) min_nz = std::min(min_nz, v);
-    const size_t NG = std::min<size_t>(size_t(p->ovl_groups), min_nx);
+    const size_t NG = std::min<size_t>(size_t(inverse && p->tuned_groups_inv > 0 ? p->tuned_groups_inv : p->ovl_groups), min_nx);
+    if (inverse) return build_overlapped_pencil_inverse(p, sc, NG);
     const size_t want_chunks = size_t(p->tuned_chunks[0] > 0 ? p->tuned_chunks[0] : p->ovl_chunks);
     const size_t NS = min_nz >= 32 * want_chunks ? want_chunks : (min_nz >= 32 ? 2 : 1);
     Split groups, chunks;
@@ -1650,11 +1826,15 @@ static int get_schedule(dfft_plan_s* p, int inverse, int d, Schedule** out) {
         const bool streams = p->cfg.send_method == DFFT_SEND_STREAMS || (p->g.decomp == DFFT_PENCIL && p->cfg.send_method2 == DFFT_SEND_STREAMS);
         const bool seq_won = p->tuned_seq[inverse ? 1 : 0] != 0;
         const bool want_overlap = streams && d == 3 && p->P > 1 && p->g.decomp == DFFT_SLAB_ZY_THEN_X && p->direct2 && p->xchg_ctas >= 0 && !seq_won;
-        const bool want_pencil_overlap = streams && d == 3 && !inverse && p->g.decomp == DFFT_PENCIL && p->direct1 && p->direct2 &&
-                                         p->grp[1].size() > 1 && p->grp[2].size() > 1 && p->xchg_ctas >= 0 && pencil_overlap_enabled() && !seq_won;
+        // pencil: forward on a grid with two real transpositions by default (measured: profiles/r02/8gpu_b); every other
+        // combination (inverse, p1 or p2 == 1) only once dfft_plan_tune has measured it faster than the sequential schedule
+        const bool both_multi = p->grp[1].size() > 1 && p->grp[2].size() > 1;
+        const bool tuned = p->tuned_ctas[inverse ? 1 : 0] != -2;
+        const bool want_pencil_overlap = streams && d == 3 && p->g.decomp == DFFT_PENCIL && p->direct1 && p->direct2 && p->P > 1 && p->xchg_ctas >= 0 &&
+                                         pencil_overlap_enabled() && !seq_won && ((both_multi && !inverse) || tuned || pencil_overlap_mode() == 2);
         int rc;
         if (want_overlap) rc = build_overlapped_slab(p, inverse ? 1 : 0, sc);
-        else if (want_pencil_overlap) rc = build_overlapped_pencil(p, sc);
+        else if (want_pencil_overlap) rc = build_overlapped_pencil(p, inverse ? 1 : 0, sc);
         else rc = build_schedule(p, inverse ? 1 : 0, d, sc);
         if (rc) return rc;
         if (g_view_error) return fail(DFFT_ERR_STATE, "internal: segments of one view disagree on the axis stride");
@@ -2222,14 +2402,18 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
     const bool streams = p->cfg.send_method == DFFT_SEND_STREAMS || (p->g.decomp == DFFT_PENCIL && p->cfg.send_method2 == DFFT_SEND_STREAMS);
     const bool has_overlap = streams && p->P > 1 && p->xchg_ctas >= 0 &&
                              ((p->g.decomp == DFFT_SLAB_ZY_THEN_X && p->direct2) ||
-                              (p->g.decomp == DFFT_PENCIL && !inverse && p->direct1 && p->direct2 && p->grp[1].size() > 1 && p->grp[2].size() > 1 &&
-                               pencil_overlap_enabled()));
+                              (p->g.decomp == DFFT_PENCIL && p->direct1 && p->direct2 && pencil_overlap_enabled()));
+    const bool pencil_inv = inverse && p->g.decomp == DFFT_PENCIL;
     const int groups_default = p->ovl_groups, chunks_default = p->ovl_chunks;
     if (has_overlap) {
         const int cta_list[] = {sms / 3, sms / 2, (2 * sms) / 3, (5 * sms) / 6, sms, 2 * sms};
         for (int c : cta_list) {
+            if (pencil_inv) {  // plane groups of the y / z passes; the x pass is not chunked
+                for (int g_ : {2, 4, 8}) cands.push_back({0, c, g_, 0});
+                continue;
+            }
             for (int ch : {4, 8}) {
-                if (inverse) cands.push_back({0, c, 1, ch});  // the inverse has no plane groups (the exchanging x pass comes first)
+                if (inverse) cands.push_back({0, c, 1, ch});  // the slab inverse has no plane groups (the exchanging x pass comes first)
                 else
                     for (int g_ : {1, 2, 4}) cands.push_back({0, c, g_, ch});
             }
@@ -2250,6 +2434,7 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
         p->tuned_ctas[dir] = c.seq ? -2 : c.ctas;
         p->tuned_chunks[dir] = c.seq ? 0 : c.chunks;
         if (!inverse) p->ovl_groups = (!c.seq && c.groups > 0) ? c.groups : groups_default;
+        else if (pencil_inv) p->tuned_groups_inv = c.seq ? 0 : c.groups;
         p->sched[dir][2] = Schedule();
     };
     int best = 0;
@@ -2350,7 +2535,10 @@ int dfft_plan_describe(dfft_plan_t p, int inverse, int d, char* buf, size_t capa
     for (const Step& s_ : sc.steps) {
         if (!first) o += ",";
         first = false;
-        o += "{\"type\":" + std::to_string(int(s_.type)) + ",\"label\":\"" + s_.label + "\",\"stream\":" + std::to_string(s_.stream);
+        o += "{\"type\":" + std::to_string(int(s_.type)) + ",\"label\":\"" + s_.label + "\",\"stream\":" + std::to_string(s_.stream) +
+             ",\"record\":" + std::to_string(s_.record) + ",\"waits\":[";
+        for (size_t w = 0; w < s_.waits.size(); ++w) o += (w ? "," : "") + std::to_string(s_.waits[w]);
+        o += "]";
         if (s_.type == STEP_PASS) {
             o += ",\"kind\":" + std::to_string(int(s_.kind)) + ",\"log2n\":" + std::to_string(s_.log2n) + ",\"A0\":" + std::to_string(s_.prm.A0) +
                  ",\"A1\":" + std::to_string(s_.prm.A1) + ",\"B\":" + std::to_string(s_.prm.B) + ",\"inverse\":" + std::to_string(s_.prm.inverse) +
@@ -2359,7 +2547,10 @@ int dfft_plan_describe(dfft_plan_t p, int inverse, int d, char* buf, size_t capa
             o += ",\"out\":";
             json_view(o, s_.prm.out, p->tabs);
         } else if (s_.type == STEP_RENDEZVOUS) {
-            o += ",\"group\":" + std::to_string(s_.group);
+            o += ",\"group\":" + std::to_string(s_.group) + ",\"phase_id\":" + std::to_string(s_.phase_id) + ",\"members\":[";
+            const std::vector<int>& G = p->grp[s_.group];
+            for (size_t q = 0; q < G.size(); ++q) o += (q ? "," : "") + std::to_string(G[q]);
+            o += "]";
         } else {
             o += ",\"group\":" + std::to_string(s_.group) + ",\"send_slot\":" + std::to_string(s_.send_slot) + ",\"recv_slot\":" + std::to_string(s_.recv_slot) + ",\"peers\":[";
             const std::vector<int>& G = p->grp[s_.group];

@@ -246,10 +246,14 @@ def main(argv=None):
         mx = allmax(float(err.max()))
         amp = 3.0 * np.sqrt(float(a.nx) * a.ny * a.nz)
         rel = mx / amp
+        # the k^2 coefficients amplify the rounding noise of every bin: the error of this testcase grows 4x per doubling of
+        # the grid whatever the exchange method (measured 1.0e-12, 4.6e-12, 2.4e-11, 9.2e-11 for 128^3 ... 1024^3 in double:
+        # profiles/r02/validation_sweep_n2.json), so the tolerance follows n^2 (the reference prints the number unjudged)
+        tol = max(1e-12 if f64 else 1e-5, (4e-16 if f64 else 2e-7) * float(max(a.nx, a.ny, a.nz)) ** 2)
         if rank == 0:
             print(f"Result (avg): {float(s[0] / s[1])}")
             print(f"Result (max): {mx}")
-            print(f"Result (max, relative to 3*sqrt(N)): {rel:.3e}  tolerance {max(tol, 1e-12):g}")
+            print(f"Result (max, relative to 3*sqrt(N)): {rel:.3e}  tolerance {tol:.3g}")
         status = int(rel >= tol)
     plan.destroy()
     comm.destroy()

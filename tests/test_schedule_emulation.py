@@ -57,6 +57,75 @@ class Memory:
         raise KeyError(hex(addr))
 
 
+class Ordering:
+    """Happens-before check of a set of per-rank step lists (what the lock-step replay cannot see: a step that runs on
+    another plan stream than its producer is only ordered behind it through an event, and a step that reads what a peer
+    stored only through a rendezvous).  Per rank: step k's ancestors = the previous step on its stream + the steps that
+    recorded the events it waits for (the auxiliary streams fork from the caller's stream before step 0).  Across ranks:
+    everything before rank a's j-th rendezvous of a group happens before everything after rank b's j-th rendezvous of
+    that group.  Every read-after-write and write-after-read on slot memory must be covered by one of the two."""
+
+    def __init__(self, scheds):
+        self.scheds = scheds
+        self.anc, self.rdv = [], []  # per rank: ancestor bit masks; {(phase_id): [step indices]}
+        for sc in scheds:
+            anc, last, recorded, rdv = [], {}, {}, {}
+            for k, st in enumerate(sc["steps"]):
+                preds = [last[st["stream"]]] if st["stream"] in last else []
+                for w in st["waits"]:
+                    assert w in recorded, f"rank {sc['rank']} step {k} ({st['label']}) waits for event {w} that no earlier step records"
+                    preds.append(recorded[w])
+                m = 0
+                for q in preds:
+                    m |= anc[q] | (1 << q)
+                anc.append(m)
+                if st["record"] >= 0:
+                    recorded[st["record"]] = k
+                last[st["stream"]] = k
+                if st["type"] == 1:
+                    rdv.setdefault(st["phase_id"], []).append(k)
+            self.anc.append(anc)
+            self.rdv.append(rdv)
+        self.last_w, self.last_r = {}, {}
+
+    def before(self, a, ka, b, kb):
+        """step ka of rank a happens before step kb of rank b"""
+        if a == b:
+            return ka == kb or bool(self.anc[a][kb] >> ka & 1)
+        for g, mine in self.rdv[a].items():
+            theirs = self.rdv[b].get(g, [])
+            if b not in self.scheds[a]["steps"][mine[0]]["members"]:
+                continue
+            for ra, rb in zip(mine, theirs):
+                if (ra == ka or self.anc[a][ra] >> ka & 1) and (rb == kb or self.anc[b][kb] >> rb & 1):
+                    return True
+        return False
+
+    def _tables(self, key, size):
+        if key not in self.last_w:
+            self.last_w[key] = np.full((2, size), -1, dtype=np.int64)
+            self.last_r[key] = np.full((2, size), -1, dtype=np.int64)
+        return self.last_w[key], self.last_r[key]
+
+    def read(self, r, k, key, size, idx):
+        lw, lr = self._tables(key, size)
+        idx = np.asarray(idx).ravel()
+        for q, kq in {(int(a), int(b)) for a, b in zip(*lw[:, idx])} - {(-1, -1)}:
+            assert self.before(q, kq, r, k), (f"rank {r} step {k} ({self.scheds[r]['steps'][k]['label']}) reads what rank {q} step {kq} "
+                                              f"({self.scheds[q]['steps'][kq]['label']}) wrote, without an event / rendezvous path between them")
+        lr[0, idx], lr[1, idx] = r, k
+
+    def write(self, r, k, key, size, idx):
+        lw, lr = self._tables(key, size)
+        idx = np.asarray(idx).ravel()
+        for q, kq in {(int(a), int(b)) for a, b in zip(*lr[:, idx])} - {(-1, -1), (r, k)}:
+            assert self.before(q, kq, r, k), (f"rank {r} step {k} ({self.scheds[r]['steps'][k]['label']}) overwrites what rank {q} step {kq} "
+                                              f"({self.scheds[q]['steps'][kq]['label']}) reads, without an event / rendezvous path between them")
+        for q, kq in {(int(a), int(b)) for a, b in zip(*lw[:, idx])} - {(-1, -1), (r, k)}:
+            assert self.before(q, kq, r, k), f"rank {r} step {k} overwrites rank {q} step {kq}'s output without ordering"
+        lw[0, idx], lw[1, idx] = r, k
+
+
 def view_indices(view, A0, A1, N, B, user_base=None):
     """flat (array, index) for every element (a0, a1, n, b) of a view, as index arrays per segment"""
     out = []
@@ -75,10 +144,12 @@ def view_indices(view, A0, A1, N, B, user_base=None):
     return out
 
 
-def run_case(P, decomp, transform, shape, p1, p2, comm_method, send_method, inverse, d):
+def run_case(P, decomp, transform, shape, p1, p2, comm_method, send_method, inverse, d, mutate=None):
     nx, ny, nz = shape
     c2c = transform == dfft.C2C
     scheds = [describe(r, P, decomp, transform, shape, p1, p2, comm_method, send_method, inverse, d) for r in range(P)]
+    if mutate:
+        mutate(scheds)  # negative tests: break the schedules on purpose
     mems = []
     lay = lambda r, w: dfft.layout(decomp, transform, nx, ny, nz, p1, p2, r, w)
     # global data and per-rank user buffers (real buffers are stored as complex pairs, like the kernels read them)
@@ -112,6 +183,7 @@ def run_case(P, decomp, transform, shape, p1, p2, comm_method, send_method, inve
             uout.append(mem.add(USER_OUT + (r << 48), nreal if c2c else nreal // 2))
     nsteps = len(scheds[0]["steps"])
     assert all(len(s["steps"]) == nsteps for s in scheds)
+    order = Ordering(scheds)
     # hazard bookkeeping: a slot written by another rank may only be read after a later rendezvous of the owner,
     # and nobody may write into a peer's slot before its own entry rendezvous (previous exec finished everywhere)
     slot_owner = {}
@@ -143,7 +215,8 @@ def run_case(P, decomp, transform, shape, p1, p2, comm_method, send_method, inve
                     assert mine["rcount"] == peer["scount"]
                     src, so = mem.resolve(sb + peer["soff"] * 16)
                     dst, do = mem.resolve(rb + mine["roff"] * 16)
-                    pending.append((dst, do, src[so:so + peer["scount"]].copy()))
+                    order.read(r, k, id(src), src.size, np.arange(so, so + peer["scount"]))
+                    pending.append((dst, do, src[so:so + peer["scount"]].copy(), q))  # lands in q's stream order (ncclRecv)
                 continue
             N = 1 << st["log2n"]
             A0, A1, B = st["A0"], st["A1"], st["B"]
@@ -168,34 +241,39 @@ def run_case(P, decomp, transform, shape, p1, p2, comm_method, send_method, inve
                 for base, ns, off in view_indices(st["in"], A0, A1, N, B, ub_in):
                     arr, o = mem.resolve(base)
                     data[:, :, ns, :] = arr[o + off]
+                    order.read(r, k, id(arr), arr.size, o + off)
                 res = np.fft.ifft(data, axis=2) * N if st["inverse"] else np.fft.fft(data, axis=2)
                 for base, ns, off in view_indices(st["out"], A0, A1, N, B, ub_out):
                     arr, o = mem.resolve(base)
-                    pending.append((arr, o + off, res[:, :, ns, :]))
+                    pending.append((arr, o + off, res[:, :, ns, :], r))
             elif kind == 2:  # R2C: N complex = 2N reals in, N+1 complex out
                 data = np.zeros((A0, A1, N, 1), dtype=np.complex128)
                 for base, ns, off in view_indices(st["in"], A0, A1, N, 1, ub_in):
                     arr, o = mem.resolve(base)
                     data[:, :, ns, :] = arr[o + off]
+                    order.read(r, k, id(arr), arr.size, o + off)
                 reals = np.ascontiguousarray(data[..., 0]).view(np.float64)  # (A0, A1, 2N)
                 res = np.fft.rfft(reals, axis=2)[..., None]
                 for base, ns, off in view_indices(st["out"], A0, A1, N + 1, 1, ub_out):
                     arr, o = mem.resolve(base)
-                    pending.append((arr, o + off, res[:, :, ns, :]))
+                    pending.append((arr, o + off, res[:, :, ns, :], r))
             else:  # C2R
                 data = np.zeros((A0, A1, N + 1, 1), dtype=np.complex128)
                 for base, ns, off in view_indices(st["in"], A0, A1, N + 1, 1, ub_in):
                     arr, o = mem.resolve(base)
                     data[:, :, ns, :] = arr[o + off]
+                    order.read(r, k, id(arr), arr.size, o + off)
                 reals = np.fft.irfft(data[..., 0], n=2 * N, axis=2) * (2 * N)
                 res = np.ascontiguousarray(reals).view(np.complex128)[..., None]
                 for base, ns, off in view_indices(st["out"], A0, A1, N, 1, ub_out):
                     arr, o = mem.resolve(base)
-                    pending.append((arr, o + off, res[:, :, ns, :]))
-        for arr, idx, val in pending:  # stores of step k land after every rank's loads of step k
+                    pending.append((arr, o + off, res[:, :, ns, :], r))
+        for arr, idx, val, who in pending:  # stores of step k land after every rank's loads of step k
             if isinstance(idx, (int, np.integer)):
+                order.write(who, k, id(arr), arr.size, np.arange(idx, idx + val.size))
                 arr[idx:idx + val.size] = val
             else:
+                order.write(who, k, id(arr), arr.size, idx)
                 arr[idx] = val
     worst = 0.0
     for r in range(P):
@@ -293,12 +371,60 @@ def test_block_width_follows_tile_width(shape, P, transform):
     (8, (16, 32, 256), 2, 4, dfft.C2C), (8, (32, 16, 64), 4, 2, dfft.R2C), (4, (8, 8, 128), 2, 2, dfft.C2C),
     (8, (16, 16, 1024), 2, 4, dfft.R2C), (8, (16, 8, 2048), 2, 4, dfft.C2C), (8, (16, 16, 2048), 4, 2, dfft.R2C)])
 def test_overlapped_pencil_schedule(P, shape, p1, p2, transform, monkeypatch):
-    """overlapped pencil schedule (SendMethod Streams), forward"""
-    monkeypatch.setenv("DFFT_PENCIL_OVERLAP", "1")
-    assert run_case(P, PE, transform, shape, p1, p2, P2P, STREAMS, 0, 3) < 1e-12
-    sched = describe(0, P, PE, transform, shape, p1, p2, P2P, STREAMS, 0, 3)
-    assert sched["overlapped"] and {s["stream"] for s in sched["steps"]} == {0, 1, 2}
-    # the inverse stays on the sequential schedule; DFFT_PENCIL_OVERLAP=0 switches the forward one off as well
+    """overlapped pencil schedules (SendMethod Streams), forward and inverse, blocked and plain hand-over layouts.
+    DFFT_PENCIL_OVERLAP=2 builds them without the plan-time measurement that normally has to select the inverse one."""
+    monkeypatch.setenv("DFFT_PENCIL_OVERLAP", "2")
+    for inverse in (0, 1):
+        assert run_case(P, PE, transform, shape, p1, p2, P2P, STREAMS, inverse, 3) < 1e-12
+        sched = describe(0, P, PE, transform, shape, p1, p2, P2P, STREAMS, inverse, 3)
+        assert sched["overlapped"] and {s["stream"] for s in sched["steps"]} == {0, 1, 2}
+    monkeypatch.setenv("DFFT_BLOCKED_INV", "0")
     assert run_case(P, PE, transform, shape, p1, p2, P2P, STREAMS, 1, 3) < 1e-12
+    monkeypatch.delenv("DFFT_BLOCKED_INV")
+    monkeypatch.setenv("DFFT_OVL_GROUPS", "3")
+    assert run_case(P, PE, transform, shape, p1, p2, P2P, STREAMS, 1, 3) < 1e-12
+    # default: forward overlapped, the inverse waits for dfft_plan_tune; DFFT_PENCIL_OVERLAP=0 switches both off
+    monkeypatch.setenv("DFFT_PENCIL_OVERLAP", "1")
+    assert describe(0, P, PE, transform, shape, p1, p2, P2P, STREAMS, 0, 3)["overlapped"]
+    assert not describe(0, P, PE, transform, shape, p1, p2, P2P, STREAMS, 1, 3)["overlapped"]
     monkeypatch.setenv("DFFT_PENCIL_OVERLAP", "0")
     assert not describe(0, P, PE, transform, shape, p1, p2, P2P, STREAMS, 0, 3)["overlapped"]
+    assert not describe(0, P, PE, transform, shape, p1, p2, P2P, STREAMS, 1, 3)["overlapped"]
+
+
+@pytest.mark.parametrize("p1,p2", [(1, 4), (4, 1), (1, 2), (2, 1)])
+@pytest.mark.parametrize("transform", [dfft.C2C, dfft.R2C])
+def test_overlapped_pencil_on_degenerate_grids(p1, p2, transform, monkeypatch):
+    """a pencil grid with p1 == 1 or p2 == 1 has one local transposition; the overlapped schedules still hold (what
+    dfft_plan_tune may select there, and what a 2-GPU box can run)"""
+    P = p1 * p2
+    assert not describe(0, P, PE, transform, (16, 32, 512), p1, p2, P2P, STREAMS, 0, 3)["overlapped"]
+    monkeypatch.setenv("DFFT_PENCIL_OVERLAP", "2")
+    for inverse in (0, 1):
+        assert describe(0, P, PE, transform, (16, 32, 512), p1, p2, P2P, STREAMS, inverse, 3)["overlapped"]
+        assert run_case(P, PE, transform, (16, 32, 512), p1, p2, P2P, STREAMS, inverse, 3) < 1e-12
+
+
+def _drop(kind):
+    """schedule mutation: remove the event waits of every step / turn every rendezvous of a transposition into a no-op"""
+    def mutate(scheds):
+        for sc in scheds:
+            for st in sc["steps"]:
+                if kind == "waits" and st["stream"] != 0:
+                    st["waits"] = []
+                if kind == "rendezvous" and st["type"] == 1 and st["group"] != 0:
+                    st["members"] = [sc["rank"]]
+    return mutate
+
+
+@pytest.mark.parametrize("decomp,shape,p1,p2", [(SL, (32, 16, 256), 4, 1), (PE, (16, 32, 256), 2, 2)])
+@pytest.mark.parametrize("inverse", [0, 1])
+@pytest.mark.parametrize("kind", ["waits", "rendezvous"])
+def test_ordering_check_catches_missing_edges(decomp, shape, p1, p2, inverse, kind, monkeypatch):
+    """the happens-before check of the replay is not vacuous: an overlapped schedule without its event waits, or without
+    the rendezvous of a transposition, is rejected (the data-flow replay alone would still produce the right numbers)"""
+    monkeypatch.setenv("DFFT_PENCIL_OVERLAP", "2")
+    P = p1 * p2
+    assert run_case(P, decomp, dfft.C2C, shape, p1, p2, P2P, STREAMS, inverse, 3) < 1e-12
+    with pytest.raises(AssertionError, match="without|before"):
+        run_case(P, decomp, dfft.C2C, shape, p1, p2, P2P, STREAMS, inverse, 3, mutate=_drop(kind))
