@@ -962,7 +962,9 @@ static int build_overlapped_slab(dfft_plan_s* p, int inverse, Schedule& sc) {
 
     // plane groups (of my x planes) and z chunks
     Split groups, chunks;
-    const size_t NG = std::min<size_t>(size_t(p->ovl_groups), nx_p);
+    size_t min_nx = nx;  // the same number of plane groups (and steps) on every rank, also for uneven splits of x
+    for (size_t v : g.sx.size) min_nx = std::min(min_nx, v);
+    const size_t NG = std::min<size_t>(size_t(p->ovl_groups), std::max<size_t>(min_nx, 1));
     const size_t want_chunks = size_t(p->tuned_chunks[inverse ? 1 : 0] > 0 ? p->tuned_chunks[inverse ? 1 : 0] : p->ovl_chunks);
     const size_t NS = nzc >= 32 * want_chunks ? want_chunks : (nzc >= 32 ? 2 : 1);
     groups.make(nx_p, NG);

