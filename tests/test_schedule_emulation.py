@@ -22,12 +22,13 @@ from oracle import dft_oracle as O
 USER_IN, USER_OUT = 1 << 60, 1 << 61  # synthetic address ranges of the caller's buffers
 
 
-def describe(rank, P, decomp, transform, shape, p1, p2, comm_method, send_method, inverse, d):
+def describe(rank, P, decomp, transform, shape, p1, p2, comm_method, send_method, inverse, d, prec=None):
+    prec = dfft.F64 if prec is None else prec
     comm = C.c_void_p()
     check(lib().dfft_comm_create_dry(rank, P, C.byref(comm)))
     cfg = _lib.dfft_config(1, 0, comm_method, send_method, None, comm_method, send_method)
     plan = C.c_void_p()
-    check(lib().dfft_plan_create(comm, C.byref(cfg), decomp, dfft.F64, transform, shape[0], shape[1], shape[2], p1, p2, 1, C.byref(plan)))
+    check(lib().dfft_plan_create(comm, C.byref(cfg), decomp, prec, transform, shape[0], shape[1], shape[2], p1, p2, 1, C.byref(plan)))
     need = C.c_size_t()
     check(lib().dfft_plan_describe(plan, inverse, d, None, 0, C.byref(need)))
     buf = C.create_string_buffer(need.value)
@@ -39,10 +40,12 @@ def describe(rank, P, decomp, transform, shape, p1, p2, comm_method, send_method
 
 
 class Memory:
-    """complex128 arrays keyed by synthetic base address"""
+    """complex128 arrays keyed by synthetic base address; `es` = bytes per complex element of the plan under test (the
+    replay always computes in complex128, only the address arithmetic follows the plan's precision)"""
 
-    def __init__(self):
+    def __init__(self, es=16):
         self.regions = []  # (base_bytes, array)
+        self.es = es
 
     def add(self, base, nelem):
         arr = np.zeros(nelem, dtype=np.complex128)
@@ -51,9 +54,9 @@ class Memory:
 
     def resolve(self, addr):
         for base, arr in self.regions:
-            if base <= addr < base + arr.size * 16:
-                assert (addr - base) % 16 == 0
-                return arr, (addr - base) // 16
+            if base <= addr < base + arr.size * self.es:
+                assert (addr - base) % self.es == 0
+                return arr, (addr - base) // self.es
         raise KeyError(hex(addr))
 
 
@@ -144,10 +147,11 @@ def view_indices(view, A0, A1, N, B, user_base=None):
     return out
 
 
-def run_case(P, decomp, transform, shape, p1, p2, comm_method, send_method, inverse, d, mutate=None):
+def run_case(P, decomp, transform, shape, p1, p2, comm_method, send_method, inverse, d, mutate=None, prec=None):
     nx, ny, nz = shape
     c2c = transform == dfft.C2C
-    scheds = [describe(r, P, decomp, transform, shape, p1, p2, comm_method, send_method, inverse, d) for r in range(P)]
+    scheds = [describe(r, P, decomp, transform, shape, p1, p2, comm_method, send_method, inverse, d, prec) for r in range(P)]
+    es = scheds[0]["esize"]
     if mutate:
         mutate(scheds)  # negative tests: break the schedules on purpose
     mems = []
@@ -159,11 +163,11 @@ def run_case(P, decomp, transform, shape, p1, p2, comm_method, send_method, inve
     else:
         xg = O.real_input(shape)
         spec = O.fft_r2c(xg, d)
-    mem = Memory()
+    mem = Memory(es)
     for r in range(P):
         sc = scheds[r]
         for s_ in range(sc["nslots"]):
-            mem.add(sc["slots"][s_][r], sc["slot_bytes"] // 16)
+            mem.add(sc["slots"][s_][r], sc["slot_bytes"] // es)
     uin, uout = [], []
     for r in range(P):
         isz, ist = lay(r, 0)
@@ -213,8 +217,8 @@ def run_case(P, decomp, transform, shape, p1, p2, comm_method, send_method, inve
                     rb = scheds[q]["slots"][st["recv_slot"]][q]
                     mine = [pp for pp in scheds[q]["steps"][k]["peers"] if pp["rank"] == r][0]
                     assert mine["rcount"] == peer["scount"]
-                    src, so = mem.resolve(sb + peer["soff"] * 16)
-                    dst, do = mem.resolve(rb + mine["roff"] * 16)
+                    src, so = mem.resolve(sb + peer["soff"] * es)
+                    dst, do = mem.resolve(rb + mine["roff"] * es)
                     order.read(r, k, id(src), src.size, np.arange(so, so + peer["scount"]))
                     pending.append((dst, do, src[so:so + peer["scount"]].copy(), q))  # lands in q's stream order (ncclRecv)
                 continue
@@ -450,12 +454,14 @@ def random_case(rng):
     if rng.random() < 0.2: env["DFFT_N1_LAYOUT"] = rng.choice(["0", "1"])
     if rng.random() < 0.2: env["DFFT_XCHG_CTAS"] = rng.choice(["0", "-1", "32"])
     return dict(P=P, decomp=decomp, transform=rng.choice([dfft.C2C, dfft.R2C]), shape=(nx, ny, nz), p1=p1, p2=p2, comm_method=rng.choice([P2P, P2P, A2A]),
-                send_method=rng.choice([SYNC, STREAMS, STREAMS]), inverse=rng.choice([0, 1]), d=rng.choice([1, 2, 3, 3, 3]) if decomp == PE else 3), env
+                send_method=rng.choice([SYNC, STREAMS, STREAMS]), inverse=rng.choice([0, 1]), d=rng.choice([1, 2, 3, 3, 3]) if decomp == PE else 3,
+                prec=rng.choice([dfft.F64, dfft.F32])), env
 
 
 @pytest.mark.parametrize("seed", range(8))
 def test_random_schedules(seed, monkeypatch):
-    """Seeded random sweep over rank counts 1-8 (uneven splits included), decompositions, grids, shapes, methods, directions,
+    """Seeded random sweep over rank counts 1-8 (uneven splits included), decompositions, grids, shapes, precisions (the
+    block widths of the hand-over layouts follow the tile widths, which differ between float and double), methods, directions,
     partial depths and the layout / overlap knobs; 2000 such cases ran clean offline when the sweep was written (it found
     the plane-group count of the overlapped slab schedule differing between ranks for uneven splits of x)."""
     import random
