@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -2426,11 +2427,7 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
         p->tune_report = "sequential schedule (no alternatives for this plan)";
         return 0;
     }
-    cudaEvent_t e0, e1;
-    CK_CUDA(cudaEventCreate(&e0));
-    CK_CUDA(cudaEventCreate(&e1));
     const bool was_timing = p->timing;
-    p->timing = false;
     auto apply = [&](const Cand& c) {
         p->tuned_seq[dir] = c.seq;
         p->tuned_ctas[dir] = c.seq ? -2 : c.ctas;
@@ -2439,6 +2436,23 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
         else if (pencil_inv) p->tuned_groups_inv = c.seq ? 0 : c.groups;
         p->sched[dir][2] = Schedule();
     };
+    // whatever way this function is left: events destroyed, the phase timer back on, and — on an error in the middle of
+    // the measurements — the plan back on the sequential schedule
+    struct Cleanup {
+        std::function<void()> f;
+        ~Cleanup() { f(); }
+    };
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool finished = false;
+    Cleanup cleanup{[&] {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        p->timing = was_timing;
+        if (!finished) apply(cands[0]);
+    }};
+    CK_CUDA(cudaEventCreate(&e0));
+    CK_CUDA(cudaEventCreate(&e1));
+    p->timing = false;
     int best = 0;
     double best_ms = 1e30;
     std::string rep;
@@ -2467,10 +2481,8 @@ int dfft_plan_tune(dfft_plan_t p, void* out, const void* in, int inverse, int re
         if (worst < best_ms) { best_ms = worst; best = int(k); }
     }
     apply(cands[best]);
+    finished = true;
     (void)chunks_default;
-    p->timing = was_timing;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     p->tune_report = std::string(inverse ? "inverse: " : "forward: ") + rep + " -> " +
                      cand_name(cands[best].seq, cands[best].ctas, cands[best].groups, cands[best].chunks);
     return best;
