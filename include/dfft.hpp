@@ -27,11 +27,20 @@ struct GlobalSize {
     size_t Nx, Ny, Nz, Nz_out;
 };
 struct Partition { size_t P1, P2; };
-struct Slab_Partition : public Partition { explicit Slab_Partition(size_t P1_) { P1 = P1_; P2 = 1; } };
+struct Slab_Partition : public Partition { Slab_Partition(size_t P1_) { P1 = P1_; P2 = 1; } };
 struct Pencil_Partition : public Partition { Pencil_Partition(size_t P1_, size_t P2_) { P1 = P1_; P2 = P2_; } };
 
 struct Partition_Dimensions {
     std::vector<size_t> size_x, size_y, size_z, start_x, start_y, start_z;
+    // params.hpp:60-64: appends the running sums of the three size lists to the start lists
+    void computeOffsets() {
+        const std::vector<size_t>* sizes[3] = {&size_x, &size_y, &size_z};
+        std::vector<size_t>* starts[3] = {&start_x, &start_y, &start_z};
+        for (int a = 0; a < 3; ++a) {
+            size_t at = 0;
+            for (size_t v : *sizes[a]) { starts[a]->push_back(at); at += v; }
+        }
+    }
 };
 
 enum CommunicationMethod { Peer2Peer, All2All };
@@ -127,6 +136,8 @@ public:
     void initFFT(GlobalSize* global_size, Partition* /*partition*/, bool allocate = true) override {
         this->create(DFFT_SLAB_Z_THEN_YX, global_size, size_t(this->pcnt), 1, allocate);
     }
+    // the override above hides the base's two-argument form (mpicufft_slab_z_then_yx.hpp:34-35 declares both)
+    void initFFT(GlobalSize* global_size, bool allocate = true) { initFFT(global_size, nullptr, allocate); }
 };
 
 template <typename T>

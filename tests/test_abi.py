@@ -149,6 +149,20 @@ def test_cpp_shim_header_compiles():
         subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), src], check=True)
 
 
+def test_cpp_shim_covers_the_reference_api_surface():
+    """tests/cpp/shim_api_surface.cpp: every public member of the reference's classes / parameter structs, in the ways its
+    test drivers use them, compiles against include/dfft.hpp; the parameter structs behave like params.hpp."""
+    import subprocess
+    import tempfile
+    src = os.path.join(ROOT, "tests", "cpp", "shim_api_surface.cpp")
+    inc = "-I" + os.path.join(ROOT, "include")
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", inc, src], check=True)
+    with tempfile.TemporaryDirectory() as td:
+        exe = os.path.join(td, "params_api")
+        subprocess.run(["g++", "-std=c++17", "-DPARAMS_ONLY", inc, src, "-o", exe], check=True)
+        assert subprocess.run([exe]).returncode == 0
+
+
 def _dry_plan(P, rank, decomp, transform, shape, p1=0, p2=1):
     comm = C.c_void_p()
     _lib.check(_lib.lib().dfft_comm_create_dry(rank, P, C.byref(comm)))
